@@ -1,0 +1,178 @@
+/* sfa_b200.h -- C ABI of libsfa_b200.so (sm_100a kernels for the sfa-numpy
+ * `micarray.modal` hot path).
+ *
+ * The reference (spatialaudio/sfa-numpy) is pure Python and has no FFI of its
+ * own; its boundary is the Python signatures of `micarray.modal.angular` and
+ * `micarray.modal.radial`.  Each entry point below names the reference
+ * function it replaces (paths relative to the reference tree).  INTEGRATION.md
+ * shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain C types only; complex128 = struct {double re, im}, complex64 =
+ *    struct {float re, im} (layout-compatible with NumPy / torch / C99).
+ *  - pointers are DEVICE pointers unless the function name ends in `_host`.
+ *  - row-major, contiguous, caller-allocated and caller-owned outputs.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *    device-pointer functions are asynchronous with respect to the host.
+ *  - return value: SFA_OK (0) or a negative sfa_status; `sfa_strerror` gives
+ *    the text.  Semantic errors that the reference raises as ValueError are
+ *    raised by the Python host layer before any launch.
+ */
+#ifndef SFA_B200_H
+#define SFA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } sfa_c128;
+typedef struct { float re, im; } sfa_c64;
+
+enum sfa_status {
+    SFA_OK = 0,
+    SFA_ERR_INVALID = -1,      /* bad argument (shape, enum, null pointer)           */
+    SFA_ERR_CUDA = -2,         /* a CUDA runtime/driver call failed (see last error) */
+    SFA_ERR_UNSUPPORTED = -3,  /* outside the supported range (e.g. order too large) */
+    SFA_ERR_WORKSPACE = -4,    /* caller workspace too small                         */
+    SFA_ERR_NO_DEVICE = -5     /* no sm_100 device                                   */
+};
+
+enum sfa_setup { SFA_OPEN = 0, SFA_CARD = 1, SFA_RIGID = 2 };       /* radial.py:146-160 */
+enum sfa_method {                                                   /* radial.py:242-264 */
+    SFA_REG_NONE = 0, SFA_REG_DISCARD = 1, SFA_REG_HARDCLIP = 2,
+    SFA_REG_SOFTCLIP = 3, SFA_REG_TIKH = 4, SFA_REG_WNG = 5
+};
+enum sfa_radial_kind {
+    SFA_SPH_WEIGHTS = 0,   /* radial.weights             radial.py:114-162 */
+    SFA_SPH_PW = 1,        /* radial.spherical_pw        radial.py:36-67   */
+    SFA_SPH_PS = 2,        /* radial.spherical_ps        radial.py:70-111  */
+    SFA_CIRC_WEIGHTS = 3,  /* radial.circ_radial_weights radial.py:393-441 */
+    SFA_CIRC_PW = 4,       /* radial.circular_pw         radial.py:317-348 */
+    SFA_CIRC_LS = 5        /* radial.circular_ls         radial.py:351-390 */
+};
+enum sfa_precision {
+    SFA_PREC_C64_3XTF32 = 0,  /* complex64 in/out, tcgen05 kind::tf32 with hi/lo split (3 passes), FP32 accumulate */
+    SFA_PREC_C128_FP64 = 1    /* complex128 in/out, FP64 FMA on the CUDA cores                                    */
+};
+
+const char* sfa_strerror(int status);
+const char* sfa_last_cuda_error(void);
+int sfa_version(void);
+/* number of SMs / compute capability of the current device (0 on success) */
+int sfa_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Instrumentation used by bench.py: kernels launched by this library so far; optional
+ * CUDA-event timing of the dominant kernel (the tcgen05 GEMM) on its launching stream. */
+long long sfa_launch_count(void);
+int sfa_prof_enable(int on);
+int sfa_prof_read(double* total_ms, long long* count);
+
+/* ---- stage 1: angular matrices ------------------------------------------------ */
+
+/* angular.sht_matrix (angular.py:12-70).  Y[q, n*n+n+m] = w[q] * Y_n^m(azi[q], colat[q]).
+ * colat has Q entries, or 1 entry when colat_is_scalar != 0 (angular.py:68 broadcast).
+ * weights may be NULL (ones, angular.py:62-63).  Y: [Q, (N+1)^2]. */
+int sfa_sht_matrix(int N, int64_t Q, const double* azi, const double* colat, int colat_is_scalar,
+                   const double* weights, sfa_c128* Y, void* stream);
+
+/* angular.cht_matrix (angular.py:106-150).  Psi[q, i] = w[q] * exp(1j * order[i] * pol[q]),
+ * order = [0, 1..N, -N..-1] (angular.py:147).  Psi: [Q, 2N+1]. */
+int sfa_cht_matrix(int N, int64_t Q, const double* pol, const double* weights, sfa_c128* Psi,
+                   void* stream);
+
+/* ---- stage 2: radial filters -------------------------------------------------- */
+
+/* Bytes of scratch `work` that sfa_radial_filter needs (zero-replacement worklist). */
+size_t sfa_radial_work_bytes(int kind, int N, int64_t F);
+
+/* One call = radial function (+ zero replacement) (+ regularised inverse), i.e. the
+ * reference sequence  bn = spherical_pw(N, k, r, setup); dn, hn = regularize(1/bn, a0, method)
+ * (doc/examples/modal_beamforming_rigid_spherical_array.py:34-35).
+ *   k   : [F] wavenumbers (for *_WEIGHTS kinds k is kr itself and r must be 1.0)
+ *   bn  : [F, C] out, C = N+1 (sphere) or 2N+1 (circle)
+ *   replace_zeros != 0 applies radial.replace_zeros_of_radial_function (radial.py:165-213)
+ *   method < 0: no inverse requested (dn/hn ignored, may be NULL); otherwise
+ *   dn  : [F, C] out = (1/bn) * hn,  hn: [F, C] out, double for SOFTCLIP/TIKH/WNG,
+ *         sfa_c128 for NONE/DISCARD/HARDCLIP (the reference's dtypes, radial.py:243-262)
+ *   status: device int32[4] out: [0] number of entries with |bn| < 1e-300 (before
+ *         replacement), [1] != 0 if a column had no non-zero entry (reference raises
+ *         ValueError, radial.py:209), [2] != 0 if the worklist overflowed.
+ *   work: device scratch of sfa_radial_work_bytes() bytes. */
+int sfa_radial_filter(int kind, int N, int64_t F, const double* k, double r, double rs, int setup,
+                      int replace_zeros, int method, double a0,
+                      sfa_c128* bn, sfa_c128* dn, void* hn, int32_t* status, void* work,
+                      void* stream);
+
+/* radial.replace_zeros_of_radial_function on an arbitrary [F, C] matrix whose rows are
+ * already ordered by ascending, distinct kr (the host layer sorts/deduplicates as
+ * radial.py:196 does).  status/work as above. */
+int sfa_replace_zeros(int64_t F, int C, const double* kr_sorted, sfa_c128* A, int32_t* status,
+                      void* work, size_t work_bytes, void* stream);
+
+/* radial.regularize (radial.py:216-266) on n elements. hn as in sfa_radial_filter. */
+int sfa_regularize(int64_t n, const sfa_c128* dn_in, double a0, int method, sfa_c128* dn_out,
+                   void* hn, void* stream);
+
+/* radial.repeat_n_m (radial.py:294-314): [F, N+1] -> [F, (N+1)^2]. */
+int sfa_repeat_n_m(int64_t F, int N, const sfa_c128* v, sfa_c128* out, void* stream);
+
+/* radial.diagonal_mode_mat / circ_diagonal_mode_mat without the repeat step
+ * (radial.py:285-290, 459-464): d [F, M] -> D [F, M, M] dense, zeros off the diagonal. */
+int sfa_diagonal_stack(int64_t F, int M, const sfa_c128* d, sfa_c128* D, void* stream);
+
+/* ---- stage 3: plane-wave decomposition / steering ------------------------------ */
+
+/* q_f = Y_L * diag(d_f) * Y_Q^H * X_f   for every bin f  -- the example idiom
+ *   A = matmul(matmul(Y_q, D), conj(Y_p.T)); q = matmul(A, p)
+ * (doc/examples/modal_beamforming_rigid_spherical_array.py:38-39, ..._open_circular_array.py:38-39)
+ * with the diagonal given as the per-column vector d_cols [F, M] (M = (N+1)^2 or 2N+1;
+ * = repeat_n_m(dn) for spheres, radial.py:284) or, when d_is_per_order != 0, as dn [F, N+1]
+ * which is expanded on the fly (column i -> order floor(sqrt(i))).
+ *   Y_L [L, M], Y_Q [Q, M] complex128 (Y_Q already carries the quadrature weights)
+ *   X   [F, Q, T], out [F, L, T]: sfa_c64 for SFA_PREC_C64_3XTF32, sfa_c128 for SFA_PREC_C128_FP64
+ * `work` is device scratch of sfa_pwd_work_bytes() bytes. */
+typedef struct {
+    int64_t F, L, Q, T;
+    int M;                 /* columns of Y_L / Y_Q                                  */
+    int Cd;                /* columns of d: M, or N+1 when d_is_per_order           */
+    int d_is_per_order;
+    int precision;         /* enum sfa_precision                                    */
+    int form;              /* 0 = auto, 1 = steering matrix A_f then A_f X_f, 2 = factored (two GEMMs) */
+} sfa_pwd_shape;
+
+size_t sfa_pwd_work_bytes(const sfa_pwd_shape* s);
+int sfa_pwd_apply(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* Y_Q,
+                  const sfa_c128* d, const void* X, void* out, void* work, size_t work_bytes,
+                  void* stream);
+
+/* Batched complex GEMM building block used by sfa_pwd_apply, exposed for tests:
+ *   out[b, n, m] = sum_k P[b?, n, k] * R[b, k, m]  (* rowscale[b, n] if given)
+ * complex64, 3xTF32 on tcgen05.  ldP, ldR, ldo in elements; strideP = 0 shares P. */
+int sfa_cgemm3x(int64_t B, int64_t Nn, int64_t Mm, int64_t K,
+                const sfa_c64* P, int64_t ldP, int64_t strideP,
+                const sfa_c64* R, int64_t ldR, int64_t strideR,
+                sfa_c64* out, int64_t ldo, int64_t strideO,
+                const sfa_c64* rowscale, int64_t strideS, void* stream);
+
+/* Host-buffer plane-wave decomposition: the call a reference user makes with NumPy
+ * arrays.  Creates device buffers/streams once; `run` copies X (pinned or pageable
+ * host memory) to the device in frequency chunks, computes, and copies the beams back,
+ * overlapping the three on separate streams. */
+typedef struct sfa_pwd_host_ctx sfa_pwd_host_ctx;
+int sfa_pwd_host_create(sfa_pwd_host_ctx** ctx, const sfa_pwd_shape* s, int device,
+                        int64_t chunk_bins);
+int sfa_pwd_host_set_operators(sfa_pwd_host_ctx* ctx, const sfa_c128* Y_L_host,
+                               const sfa_c128* Y_Q_host, const sfa_c128* d_host);
+int sfa_pwd_host_run(sfa_pwd_host_ctx* ctx, const void* X_host, void* out_host);
+int sfa_pwd_host_destroy(sfa_pwd_host_ctx* ctx);
+/* pinned host memory helpers for the host path */
+int sfa_host_alloc(void** p, size_t bytes);
+int sfa_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFA_B200_H */

@@ -1,0 +1,488 @@
+// Batched complex GEMM on the 5th-generation tensor cores (sm_100a):
+//
+//     out[b, n, m] = sum_k P[b|shared, n, k] * R[b, k, m]      (* rowscale[b, n])
+//
+// complex64 data, "3xTF32": every real operand x is split as x = hi + lo with
+// hi = tf32(x) (cvt.rna) and lo = x - hi; the product is accumulated in FP32 as
+// hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-22 relative).  A complex
+// product is 4 real products into two accumulators (Re, Im); the minus sign of
+// Re -= Ri*Pi uses the instruction descriptor's negate-A bit.
+//
+// This is stage 3 of the hot path: the plane-wave-decomposition/steering
+// contraction of the reference's example idiom
+//     A = matmul(matmul(Y_q, D), conj(Y_p.T)); q = matmul(A, p)
+// (doc/examples/modal_beamforming_rigid_spherical_array.py:38-39), for which
+// pwd_apply.cu issues one or two calls of this kernel per frequency chunk.
+//
+// Mapping onto the machine (one persistent CTA per SM, 320 threads):
+//   * UMMA M (128 TMEM lanes) = 128 consecutive m (time frames) of one batch b.
+//     The R^T tile [128 m x K<=64] is the A operand and lives in TENSOR MEMORY
+//     (TS-form tcgen05.mma): four "loader" warps read R straight from global
+//     memory (coalesced along m), split hi/lo in registers and write the four
+//     planes (re_hi, im_hi, re_lo, im_lo; 64 columns each) with tcgen05.st.
+//     It stays there for the whole task (b, m-tile) -> R is read exactly once.
+//   * UMMA N = 64 rows n of P per step.  P is always produced by this library
+//     (steering matrices, SH matrices), so it is stored pre-split and planar
+//     ([4 planes][n][k] fp32).  One elected thread streams it with TMA
+//     (cp.async.bulk.tensor, SWIZZLE_128B) into a 3-stage shared-memory ring in
+//     exactly the canonical K-major layout the UMMA descriptor reads.
+//   * One elected thread issues the tcgen05.mma.kind::tf32 stream:
+//     3 passes x 4 real products x K/8 k-steps per n-tile, accumulating into a
+//     double-buffered pair of TMEM accumulators (Re, Im: 64 columns each).
+//   * Four epilogue warps read the accumulators with tcgen05.ld (lane = m) and
+//     store complex64 directly: a warp writes 32 consecutive m of one row n =
+//     256 contiguous bytes per store instruction, no shared-memory transpose.
+// TMEM budget: 2 x (64 Re + 64 Im) accumulator columns + 256 operand columns = 512.
+#include <cuda.h>
+#include "sfa_common.cuh"
+
+namespace sfa {
+
+constexpr int kTileM = 128;          // m per task (TMEM lanes)
+constexpr int kTileN = 64;           // rows of P per MMA step
+constexpr int kMaxK = 64;            // complex k resident in TMEM per launch
+constexpr int kStagesB = 3;
+constexpr int kBoxK = 32;            // fp32 per 128-byte swizzle row
+constexpr int kBoxBytes = kTileN * kBoxK * 4;            // 8 KB
+constexpr int kStageBytes = 4 * 2 * kBoxBytes;           // 4 planes x 2 k-boxes = 64 KB
+constexpr int kThreads = 320;
+constexpr int kTmemCols = 512;
+constexpr int kAccCols = 2 * kTileN;                     // Re + Im per accumulator stage
+constexpr int kOperandCol0 = 2 * kAccCols;               // 256
+
+enum OutMode { OUT_C64 = 0, OUT_C64_ACCUM = 2 };
+
+struct GemmParams {
+    long long B, Nn, Mm;
+    int K;                  // <= kMaxK for this launch
+    const float2* R;        // [B][K][ldR]
+    long long ldR, strideR;
+    int p_shared;           // P has no batch dimension
+    float* out;             // float2 view
+    long long ldo, strideO; // in float2 elements
+    const float2* rowscale; // [B][Nn] or null
+    long long strideS;
+    int out_mode;
+    int m_tiles;            // ceil(Mm / 128)
+    long long tasks;        // B * m_tiles
+    int n_tiles;            // ceil(Nn / 64)
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]   (TS form, kind::tf32, cta_group::1)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+#define SFA_TMEM_ST32(taddr, v)                                                                           \
+    asm volatile(                                                                                         \
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "    \
+        "%12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, " \
+        "%31, %32};" ::"r"(taddr),                                                                        \
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), \
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),    \
+        "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),   \
+        "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])                \
+        : "memory")
+
+#define SFA_TMEM_LD32(taddr, v)                                                                            \
+    asm volatile(                                                                                          \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "  \
+        "%13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, " \
+        "[%32];"                                                                                           \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),  \
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),         \
+          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),       \
+          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),       \
+          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                            \
+        : "r"(taddr)                                                                                       \
+        : "memory")
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 version field = 1).
+// Rows are 128 bytes (32 fp32), 8-row groups are 1024 bytes apart (SBO); the
+// leading-dimension offset is unused for swizzled K-major layouts.
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);           // start address  [0,14)
+    d |= (uint64_t)1 << 16;                                 // LBO (ignored)  [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                       // SBO            [32,46)
+    d |= (uint64_t)1 << 46;                                 // version = 1    [46,48)
+    d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B   [61,64)
+    return d;
+}
+
+// Instruction descriptor: F32 accumulate, TF32 x TF32, K-major A and B.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+struct __align__(8) Barriers {
+    uint64_t b_full[kStagesB];
+    uint64_t b_empty[kStagesB];
+    uint64_t acc_full[2];
+    uint64_t acc_empty[2];
+    uint64_t a_full;
+    uint64_t a_empty;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) {
+    extern __shared__ unsigned char smem_dyn[];
+    // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack.
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* stage_base = smem;                                    // kStagesB x 64 KB
+    Barriers* bars = reinterpret_cast<Barriers*>(smem + (size_t)kStagesB * kStageBytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ksteps = (prm.K + 7) >> 3;               // MMA k-steps of 8
+    const int kboxes = (prm.K + kBoxK - 1) / kBoxK;    // TMA boxes along k (1 or 2)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStagesB; ++s) {
+            mbar_init(&bars->b_full[s], 1);
+            mbar_init(&bars->b_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bars->acc_full[a], 1);
+            mbar_init(&bars->acc_empty[a], 4);
+        }
+        mbar_init(&bars->a_full, 4);
+        mbar_init(&bars->a_empty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&bars->tmem_base)),
+                     "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer: stream P tiles =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&p_map) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long task = blockIdx.x; task < prm.tasks; task += gridDim.x) {
+                const long long b = task / prm.m_tiles;
+                const int pb = prm.p_shared ? 0 : (int)b;
+                for (int nt = 0; nt < prm.n_tiles; ++nt) {
+                    mbar_wait(&bars->b_empty[stage], phase ^ 1);
+                    unsigned char* dst = stage_base + (size_t)stage * kStageBytes;
+                    mbar_arrive_expect_tx(&bars->b_full[stage], (uint32_t)(4 * kboxes * kBoxBytes));
+                    for (int pl = 0; pl < 4; ++pl)
+                        for (int kb = 0; kb < kboxes; ++kb)
+                            tma_load_3d(&p_map, &bars->b_full[stage], dst + (pl * 2 + kb) * kBoxBytes,
+                                        kb * kBoxK, nt * kTileN, pb * 4 + pl);
+                    if (++stage == kStagesB) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kTileM, kTileN, false);
+            constexpr uint32_t idesc_neg = make_idesc(kTileM, kTileN, true);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+            for (long long task = blockIdx.x; task < prm.tasks; task += gridDim.x) {
+                mbar_wait(&bars->a_full, a_phase);
+                tcgen05_fence_after();
+                for (int nt = 0; nt < prm.n_tiles; ++nt) {
+                    mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+                    mbar_wait(&bars->b_full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sbase = smem_u32(stage_base + (size_t)stage * kStageBytes);
+                    const uint32_t d_re = tmem + acc * kAccCols;
+                    const uint32_t d_im = d_re + kTileN;
+                    uint32_t first = 0;
+#pragma unroll 1
+                    for (int pass = 0; pass < 3; ++pass) {
+                        // (A part, B part): (hi,hi) (hi,lo) (lo,hi)
+                        const int ap = (pass == 2) ? 2 : 0;       // plane offset of re within {re_hi,im_hi,re_lo,im_lo}
+                        const int bp = (pass == 1) ? 2 : 0;
+                        const uint32_t a_re = tmem + kOperandCol0 + (ap + 0) * kMaxK;
+                        const uint32_t a_im = tmem + kOperandCol0 + (ap + 1) * kMaxK;
+#pragma unroll 1
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const int kb = ks >> 2, kk = ks & 3;
+                            const uint64_t b_re = make_b_desc(sbase + ((bp + 0) * 2 + kb) * kBoxBytes + kk * 32);
+                            const uint64_t b_im = make_b_desc(sbase + ((bp + 1) * 2 + kb) * kBoxBytes + kk * 32);
+                            umma_tf32_ts(d_re, a_re + ks * 8, b_re, idesc, first);
+                            umma_tf32_ts(d_im, a_re + ks * 8, b_im, idesc, first);
+                            first = 1;
+                            umma_tf32_ts(d_re, a_im + ks * 8, b_im, idesc_neg, 1);
+                            umma_tf32_ts(d_im, a_im + ks * 8, b_re, idesc, 1);
+                        }
+                    }
+                    tcgen05_commit(&bars->b_empty[stage]);
+                    tcgen05_commit(&bars->acc_full[acc]);
+                    if (++stage == kStagesB) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_phase ^= 1;
+                    }
+                }
+                tcgen05_commit(&bars->a_empty);
+                a_phase ^= 1;
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== A-operand loaders: global -> regs -> TMEM =====================
+        const int quarter = warp & 3;                       // TMEM lane quarter this warp may touch
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        uint32_t a_phase = 0;
+        for (long long task = blockIdx.x; task < prm.tasks; task += gridDim.x) {
+            const long long b = task / prm.m_tiles;
+            const int mt = (int)(task - b * prm.m_tiles);
+            const long long m = (long long)mt * kTileM + quarter * 32 + lane;
+            const bool m_ok = m < prm.Mm;
+            const float2* src = prm.R + b * prm.strideR + (m_ok ? m : 0);
+            // wait until the MMAs of the previous task no longer read the operand columns
+            mbar_wait(&bars->a_empty, a_phase ^ 1);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                float2 v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int k = half * 32 + j;
+                    v[j] = (m_ok && k < prm.K) ? __ldg(src + (long long)k * prm.ldR) : make_float2(0.f, 0.f);
+                }
+                uint32_t w[32];
+                const uint32_t col = tmem + lane_base + kOperandCol0 + half * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w[j] = to_tf32(v[j].x);
+                SFA_TMEM_ST32(col + 0 * kMaxK, w);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j].x - __uint_as_float(to_tf32(v[j].x)));
+                SFA_TMEM_ST32(col + 2 * kMaxK, w);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w[j] = to_tf32(v[j].y);
+                SFA_TMEM_ST32(col + 1 * kMaxK, w);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j].y - __uint_as_float(to_tf32(v[j].y)));
+                SFA_TMEM_ST32(col + 3 * kMaxK, w);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->a_full);
+            a_phase ^= 1;
+        }
+    } else {
+        // ===================== epilogue: TMEM -> regs -> global =====================
+        const int quarter = warp & 3;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long task = blockIdx.x; task < prm.tasks; task += gridDim.x) {
+            const long long b = task / prm.m_tiles;
+            const int mt = (int)(task - b * prm.m_tiles);
+            const long long m = (long long)mt * kTileM + quarter * 32 + lane;
+            const bool m_ok = m < prm.Mm;
+            for (int nt = 0; nt < prm.n_tiles; ++nt) {
+                mbar_wait(&bars->acc_full[acc], acc_phase);
+                tcgen05_fence_after();
+                const uint32_t t_re = tmem + lane_base + acc * kAccCols;
+                const long long n0 = (long long)nt * kTileN;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t re[32], im[32];
+                    SFA_TMEM_LD32(t_re + half * 32, re);
+                    SFA_TMEM_LD32(t_re + kTileN + half * 32, im);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (half == 1) {
+                        // accumulator fully read -> hand it back to the MMA warp before storing
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+                    }
+                    if (m_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const long long n = n0 + half * 32 + j;
+                            if (n < prm.Nn) {
+                                float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
+                                if (prm.rowscale) {
+                                    const float2 s = __ldg(prm.rowscale + b * prm.strideS + n);
+                                    const float tr = xr * s.x - xi * s.y;
+                                    xi = xr * s.y + xi * s.x;
+                                    xr = tr;
+                                }
+                                {
+                                    float2* o = reinterpret_cast<float2*>(prm.out) + b * prm.strideO + n * prm.ldo + m;
+                                    if (prm.out_mode == OUT_C64_ACCUM) {
+                                        const float2 old = *o;
+                                        xr += old.x;
+                                        xi += old.y;
+                                    }
+                                    *o = make_float2(xr, xi);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// P planar-split layout: [batches][4 planes][Nn][Kp] fp32, Kp % 4 == 0.
+int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* Pplanar, long long Kp,
+                   int p_shared, const float2* R, long long ldR, long long strideR, float* out, long long ldo,
+                   long long strideO, int out_mode, const float2* rowscale, long long strideS,
+                   cudaStream_t st) {
+    if (B <= 0 || Nn <= 0 || Mm <= 0) return SFA_OK;
+    if (K <= 0 || K > kMaxK || (Kp & 3) || Kp < K) return SFA_ERR_INVALID;
+    if (((uintptr_t)Pplanar & 15) || ((uintptr_t)R & 7)) return SFA_ERR_INVALID;
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) return SFA_ERR_UNSUPPORTED;
+    CUtensorMap map;
+    const long long pb = p_shared ? 1 : B;
+    cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)Nn, (cuuint64_t)(4 * pb)};
+    cuuint64_t gstr[2] = {(cuuint64_t)Kp * 4, (cuuint64_t)Nn * Kp * 4};
+    cuuint32_t box[3] = {(cuuint32_t)kBoxK, (cuuint32_t)kTileN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)Pplanar, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
+        return SFA_ERR_CUDA;
+    }
+    GemmParams prm;
+    prm.B = B;
+    prm.Nn = Nn;
+    prm.Mm = Mm;
+    prm.K = K;
+    prm.R = R;
+    prm.ldR = ldR;
+    prm.strideR = strideR;
+    prm.p_shared = p_shared;
+    prm.out = out;
+    prm.ldo = ldo;
+    prm.strideO = strideO;
+    prm.rowscale = rowscale;
+    prm.strideS = strideS;
+    prm.out_mode = out_mode;
+    prm.m_tiles = (int)ceil_div(Mm, kTileM);
+    prm.tasks = B * prm.m_tiles;
+    prm.n_tiles = (int)ceil_div(Nn, kTileN);
+    const size_t smem = (size_t)kStagesB * kStageBytes + sizeof(Barriers) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SFA_CUDA_CHECK(cudaFuncSetAttribute(cgemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    long long grid = prm.tasks < sm_count() ? prm.tasks : sm_count();
+    prof_begin(st);
+    cgemm3x_kernel<<<(unsigned)grid, kThreads, smem, st>>>(map, prm);
+    prof_end(st);
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+}  // namespace sfa

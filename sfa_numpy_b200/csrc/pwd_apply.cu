@@ -1,0 +1,661 @@
+// Stage 3 orchestration: q_f = Y_L diag(d_f) Y_Q^H X_f for every frequency bin.
+//
+// Reference idiom being replaced (dense diagonal stack + three np.matmul):
+//   doc/examples/modal_beamforming_rigid_spherical_array.py:36-39
+//   doc/examples/modal_beamforming_open_circular_array.py:35-39
+//   radial.diagonal_mode_mat / repeat_n_m              micarray/modal/radial.py:269-314
+//
+// Two algebraically identical evaluation orders, chosen per shape:
+//   form 1 "steering":  A_f = sum_g d_f[g] G_g  with  G_g = sum_{m in g} Y_L[:,m] Y_Q[:,m]^H
+//                       (g = SH order n, or the column itself), then q_f = A_f X_f.
+//                       Cheapest when Q <= M and T is large (the headline config).
+//   form 2 "factored":  Z_f = d_f * (Y_Q^H X_f), q_f = Y_L Z_f.  Cheapest when T is small
+//                       or Q > M; never materialises an [F, L, Q] tensor.
+// The dense [F, M, M] diagonal stack of the reference is never built.
+//
+// c64 path: the GEMMs run on tcgen05 (cgemm3x_sm100.cu); c128 path: FP64 FMA kernels below.
+#include <stdlib.h>
+#include "sfa_common.cuh"
+
+namespace sfa {
+
+int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* Pplanar, long long Kp,
+                   int p_shared, const float2* R, long long ldR, long long strideR, float* out, long long ldo,
+                   long long strideO, int out_mode, const float2* rowscale, long long strideS,
+                   cudaStream_t st);
+
+constexpr int kOutC64 = 0, kOutAccum = 2;
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// x (double) -> hi = tf32(x), lo = float(x - hi)
+__device__ __forceinline__ void split_from_double(double x, float& hi, float& lo) {
+    hi = __uint_as_float(tf32_rna((float)x));
+    lo = (float)(x - (double)hi);
+}
+
+__device__ __forceinline__ int order_of_column(int i) {     // radial.repeat_n_m: column i -> order n
+    int n = (int)sqrtf((float)i);
+    while ((n + 1) * (n + 1) <= i) ++n;
+    while (n * n > i) --n;
+    return n;
+}
+
+// S [rows x cols] complex128 (ld) -> planar split P[4][Nn][Kp]; P(n,k) = S(n,k) or conj(S(k,n)).
+__global__ void split_planar_kernel(const double2* __restrict__ S, long long ld, int conj_transpose,
+                                    long long Nn, long long K, long long Kp, float* __restrict__ P) {
+    const long long total = Nn * Kp;
+    const long long plane = Nn * Kp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / Kp, k = i - n * Kp;
+        double re = 0.0, im = 0.0;
+        if (k < K) {
+            const double2 v = conj_transpose ? S[k * ld + n] : S[n * ld + k];
+            re = v.x;
+            im = conj_transpose ? -v.y : v.y;
+        }
+        float h, l;
+        split_from_double(re, h, l);
+        P[i] = h;
+        P[2 * plane + i] = l;
+        split_from_double(im, h, l);
+        P[plane + i] = h;
+        P[3 * plane + i] = l;
+    }
+}
+
+// d [F][Cd] complex128 -> per-column diagonal [F][M] (complex64 or complex128)
+template <class T2>
+__global__ void expand_diag_kernel(const double2* __restrict__ d, long long F, int Cd, int M, int per_order,
+                                   T2* __restrict__ out) {
+    const long long total = F * M;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i / M;
+        const int c = (int)(i - f * M);
+        const double2 v = d[f * Cd + (per_order ? order_of_column(c) : c)];
+        T2 o;
+        o.x = v.x;
+        o.y = v.y;
+        out[i] = o;
+    }
+}
+
+// G[g][l*Qp + q] = sum_{m in group g} Y_L[l,m] * conj(Y_Q[q,m])   (FP64 accumulate)
+template <class T2>
+__global__ void group_products_kernel(const double2* __restrict__ YL, const double2* __restrict__ YQ, long long L,
+                                      long long Q, long long Qp, int M, int G, int per_order,
+                                      T2* __restrict__ out) {
+    const long long total = L * Qp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long l = i / Qp, q = i - l * Qp;
+        for (int g = 0; g < G; ++g) {
+            double sr = 0.0, si = 0.0;
+            if (q < Q) {
+                const int m0 = per_order ? g * g : g;
+                const int m1 = per_order ? (g + 1) * (g + 1) : g + 1;
+                for (int m = m0; m < m1 && m < M; ++m) {
+                    const double2 a = YL[l * M + m];
+                    const double2 b = YQ[q * M + m];
+                    sr += a.x * b.x + a.y * b.y;       // a * conj(b)
+                    si += a.y * b.x - a.x * b.y;
+                }
+            }
+            T2 o;
+            o.x = sr;
+            o.y = si;
+            out[(long long)g * total + i] = o;
+        }
+    }
+}
+
+// Steering matrices of a frequency chunk, written pre-split for the tensor-core GEMM:
+//   A[f][plane][l*Qp + q] = split( sum_g d[f][g] * G[g][l*Qp+q] )
+__global__ void __launch_bounds__(256)
+steer_build_split_kernel(const float2* __restrict__ G, const double2* __restrict__ d, int Cd, int ngroups,
+                         long long f0, int nf, long long LQ, float* __restrict__ A) {
+    extern __shared__ float2 sh_d[];                    // [nf][ngroups]
+    for (int i = threadIdx.x; i < nf * ngroups; i += blockDim.x) {
+        const int f = i / ngroups, g = i - f * ngroups;
+        const double2 v = d[(f0 + f) * Cd + g];
+        sh_d[i] = make_float2((float)v.x, (float)v.y);
+    }
+    __syncthreads();
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < LQ;
+         e += (long long)gridDim.x * blockDim.x) {
+        float2 g[64];
+#pragma unroll 1
+        for (int c = 0; c < ngroups; ++c) g[c] = __ldg(G + (long long)c * LQ + e);
+        for (int f = 0; f < nf; ++f) {
+            float ar = 0.f, ai = 0.f;
+            for (int c = 0; c < ngroups; ++c) {
+                const float2 dv = sh_d[f * ngroups + c];
+                ar = fmaf(dv.x, g[c].x, ar);
+                ar = fmaf(-dv.y, g[c].y, ar);
+                ai = fmaf(dv.x, g[c].y, ai);
+                ai = fmaf(dv.y, g[c].x, ai);
+            }
+            float* o = A + (long long)f * 4 * LQ + e;
+            const float hr = __uint_as_float(tf32_rna(ar)), hi = __uint_as_float(tf32_rna(ai));
+            o[0] = hr;
+            o[LQ] = hi;
+            o[2 * LQ] = ar - hr;
+            o[3 * LQ] = ai - hi;
+        }
+    }
+}
+
+// FP64 variant: A[f][l*Q + q] complex128
+__global__ void steer_build_f64_kernel(const double2* __restrict__ G, const double2* __restrict__ d, int Cd,
+                                       int ngroups, long long f0, int nf, long long LQ,
+                                       double2* __restrict__ A) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < LQ * nf;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long f = e / LQ, i = e - f * LQ;
+        double ar = 0.0, ai = 0.0;
+        for (int c = 0; c < ngroups; ++c) {
+            const double2 dv = d[(f0 + f) * Cd + c];
+            const double2 g = G[(long long)c * LQ + i];
+            ar += dv.x * g.x - dv.y * g.y;
+            ai += dv.x * g.y + dv.y * g.x;
+        }
+        A[e] = make_double2(ar, ai);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// FP64 batched complex GEMM on the CUDA cores (c128 path):
+//   out[b,n,m] = sum_k P[b|shared][n][k] * R[b][k][m]  (* rowscale[b][n])
+// 64 (m) x 64 (n) tile per CTA, 256 threads, 4x4 complex outputs per thread.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+zgemm_kernel(long long B, long long Nn, long long Mm, long long K, const double2* __restrict__ P, long long ldP,
+             long long strideP, const double2* __restrict__ R, long long ldR, long long strideR,
+             double2* __restrict__ out, long long ldo, long long strideO, const double2* __restrict__ rowscale,
+             long long strideS) {
+    constexpr int TM = 64, TN = 64, TK = 8;
+    __shared__ double2 Rs[TK][TM];
+    __shared__ double2 Ps[TN][TK + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long m_tiles = (Mm + TM - 1) / TM, n_tiles = (Nn + TN - 1) / TN;
+    const long long tiles = B * m_tiles * n_tiles;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long b = tile / (m_tiles * n_tiles);
+        const long long rem = tile - b * m_tiles * n_tiles;
+        const long long nt = rem / m_tiles, mt = rem - nt * m_tiles;
+        const long long m0 = mt * TM, n0 = nt * TN;
+        const double2* Pb = P + b * strideP;
+        const double2* Rb = R + b * strideR;
+        double accr[4][4], acci[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) accr[i][j] = acci[i][j] = 0.0;
+        for (long long k0 = 0; k0 < K; k0 += TK) {
+            for (int e = threadIdx.x; e < TK * TM; e += 256) {
+                const int kk = e / TM, mm = e - kk * TM;
+                const long long k = k0 + kk, m = m0 + mm;
+                Rs[kk][mm] = (k < K && m < Mm) ? Rb[k * ldR + m] : make_double2(0.0, 0.0);
+            }
+            for (int e = threadIdx.x; e < TN * TK; e += 256) {
+                const int nn = e / TK, kk = e - nn * TK;
+                const long long k = k0 + kk, n = n0 + nn;
+                Ps[nn][kk] = (k < K && n < Nn) ? Pb[n * ldP + k] : make_double2(0.0, 0.0);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < TK; ++kk) {
+                double2 r[4], p[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r[j] = Rs[kk][tx * 4 + j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) p[i] = Ps[ty * 4 + i][kk];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        accr[i][j] = fma(p[i].x, r[j].x, accr[i][j]);
+                        accr[i][j] = fma(-p[i].y, r[j].y, accr[i][j]);
+                        acci[i][j] = fma(p[i].x, r[j].y, acci[i][j]);
+                        acci[i][j] = fma(p[i].y, r[j].x, acci[i][j]);
+                    }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long n = n0 + ty * 4 + i;
+            if (n >= Nn) continue;
+            double2 s = make_double2(1.0, 0.0);
+            if (rowscale) s = rowscale[b * strideS + n];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long m = m0 + tx * 4 + j;
+                if (m >= Mm) continue;
+                double xr = accr[i][j], xi = acci[i][j];
+                if (rowscale) {
+                    const double t = xr * s.x - xi * s.y;
+                    xi = xr * s.y + xi * s.x;
+                    xr = t;
+                }
+                out[b * strideO + n * ldo + m] = make_double2(xr, xi);
+            }
+        }
+    }
+}
+
+__global__ void conj_transpose_kernel(const double2* __restrict__ S, long long rows, long long cols,
+                                      double2* __restrict__ out) {   // out[c][r] = conj(S[r][c])
+    const long long total = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long c = i / rows, r = i - c * rows;
+        const double2 v = S[r * cols + c];
+        out[i] = make_double2(v.x, -v.y);
+    }
+}
+
+static unsigned grid1d(long long items, int threads = 256) {
+    long long b = ceil_div(items, threads);
+    const long long cap = (long long)sm_count() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static inline long long round_up(long long x, long long a) { return (x + a - 1) / a * a; }
+static long long gcdll(long long a, long long b) { return b ? gcdll(b, a % b) : a; }
+
+struct Plan {
+    int form;
+    long long Qp, Mp, Tld;      // padded k extents / leading dims
+    int ngroups;
+    long long fc;               // bins per chunk
+    size_t off_G, off_A, off_P1, off_P2, off_dcols, off_Z, total;
+};
+
+static double gemm_cost(double Nn, double Mm, double K, double batches) {
+    // MMA work in padded tile units plus the split-K read-modify-write traffic, in seconds (rough).
+    const double mma = ceil(Mm / 128.0) * 128.0 * ceil(Nn / 64.0) * 64.0 * ceil(K / 8.0) * 8.0 * 8.0 * 3.0;
+    const double chunks = ceil(K / 64.0);
+    const double bytes = Nn * Mm * 8.0 * (1.0 + 2.0 * (chunks - 1.0));
+    return batches * (mma / 700e12 + bytes / 6.0e12);
+}
+
+static int make_plan(const sfa_pwd_shape* s, Plan* p) {
+    if (!s || s->F < 0 || s->L <= 0 || s->Q <= 0 || s->T <= 0 || s->M <= 0 || s->Cd <= 0) return SFA_ERR_INVALID;
+    if (s->precision != SFA_PREC_C64_3XTF32 && s->precision != SFA_PREC_C128_FP64) return SFA_ERR_INVALID;
+    if (s->d_is_per_order) {
+        const int N1 = s->Cd;
+        if (N1 * N1 != s->M) return SFA_ERR_INVALID;
+    } else if (s->Cd != s->M) return SFA_ERR_INVALID;
+    const bool c64 = s->precision == SFA_PREC_C64_3XTF32;
+    p->Qp = round_up(s->Q, 4);
+    p->Mp = round_up(s->M, 4);
+    p->Tld = s->T;
+    p->ngroups = s->Cd;
+    int form = s->form;
+    if (form == 0) {
+        const double c1 = gemm_cost((double)s->L, (double)s->T, (double)s->Q, 1.0) +
+                          (double)s->L * p->Qp * (16.0 * 2.0 / 6.0e12 + 8.0 * s->Cd / 40e12);
+        const double c2 = gemm_cost((double)s->M, (double)s->T, (double)s->Q, 1.0) +
+                          gemm_cost((double)s->L, (double)s->T, (double)s->M, 1.0);
+        form = (c1 <= c2 && s->Cd <= 64) ? 1 : 2;
+    }
+    if (form == 1 && s->Cd > 64) return SFA_ERR_UNSUPPORTED;
+    p->form = form;
+    // bins per chunk: keep the per-chunk scratch around `budget` bytes and the task count a
+    // multiple of the SM count (tasks = bins * ceil(T/128)) so persistent CTAs finish together.
+    double budget = 96.0 * 1024 * 1024;
+    if (const char* e = getenv("SFA_PWD_CHUNK_MB")) budget = atof(e) * 1024 * 1024;
+    const double per_bin = (form == 1) ? (double)s->L * p->Qp * 16.0 : (double)s->M * p->Tld * (c64 ? 8.0 : 16.0);
+    const long long m_tiles = ceil_div(s->T, 128);
+    const long long base = sm_count() / gcdll(sm_count(), m_tiles);
+    long long fc = (long long)(budget / per_bin);
+    if (fc >= base) fc = fc / base * base;
+    if (fc < 1) fc = 1;
+    if (fc > s->F) fc = s->F > 0 ? s->F : 1;
+    p->fc = fc;
+    size_t off = 0;
+    p->off_G = p->off_A = p->off_P1 = p->off_P2 = p->off_dcols = p->off_Z = 0;
+    const size_t esz = c64 ? 8 : 16;
+    if (form == 1) {
+        p->off_G = off;
+        off += align_up((size_t)s->Cd * s->L * p->Qp * esz);
+        p->off_A = off;
+        off += align_up((size_t)fc * s->L * p->Qp * 16);      // 4 fp32 planes == one complex128
+    } else {
+        p->off_P1 = off;
+        off += align_up((size_t)s->M * p->Qp * 16);
+        p->off_P2 = off;
+        off += align_up((size_t)s->L * p->Mp * 16);
+        p->off_dcols = off;
+        off += align_up((size_t)fc * s->M * esz);
+        p->off_Z = off;
+        off += align_up((size_t)fc * s->M * p->Tld * esz);
+    }
+    p->total = off + 256;
+    return SFA_OK;
+}
+
+static int cgemm_splitk(long long B, long long Nn, long long Mm, long long K, const float* Pp, long long Kp,
+                        int p_shared, const float2* R, long long ldR, long long strideR, float2* out, long long ldo,
+                        long long strideO, const float2* rowscale, long long strideS, cudaStream_t st) {
+    for (long long k0 = 0; k0 < K; k0 += 64) {
+        const int kc = (int)((K - k0 < 64) ? (K - k0) : 64);
+        int rc = launch_cgemm3x(B, Nn, Mm, kc, Pp + k0, Kp, p_shared, R + k0 * ldR, ldR, strideR,
+                                reinterpret_cast<float*>(out), ldo, strideO, k0 == 0 ? kOutC64 : kOutAccum,
+                                rowscale, strideS, st);
+        if (rc != SFA_OK) return rc;
+    }
+    return SFA_OK;
+}
+
+// One-time operator preparation (independent of d and X).
+static int pwd_prepare(const sfa_pwd_shape* s, const Plan& p, const double2* yl, const double2* yq,
+                       unsigned char* w, cudaStream_t st) {
+    const long long L = s->L, Q = s->Q;
+    const int M = s->M, Cd = s->Cd;
+    const bool c64 = s->precision == SFA_PREC_C64_3XTF32;
+    const long long LQ = L * p.Qp;
+    if (p.form == 1) {
+        if (c64)
+            group_products_kernel<float2><<<grid1d(LQ), 256, 0, st>>>(yl, yq, L, Q, p.Qp, M, Cd, s->d_is_per_order,
+                                                                     reinterpret_cast<float2*>(w + p.off_G));
+        else
+            group_products_kernel<double2><<<grid1d(LQ), 256, 0, st>>>(yl, yq, L, Q, p.Qp, M, Cd, s->d_is_per_order,
+                                                                      reinterpret_cast<double2*>(w + p.off_G));
+        SFA_LAUNCH_CHECK();
+    } else if (c64) {
+        split_planar_kernel<<<grid1d((long long)M * p.Qp), 256, 0, st>>>(yq, M, 1, M, Q, p.Qp,
+                                                                        reinterpret_cast<float*>(w + p.off_P1));
+        SFA_LAUNCH_CHECK();
+        split_planar_kernel<<<grid1d(L * p.Mp), 256, 0, st>>>(yl, M, 0, L, M, p.Mp,
+                                                             reinterpret_cast<float*>(w + p.off_P2));
+        SFA_LAUNCH_CHECK();
+    } else {
+        conj_transpose_kernel<<<grid1d(Q * M), 256, 0, st>>>(yq, Q, M, reinterpret_cast<double2*>(w + p.off_P1));
+        SFA_LAUNCH_CHECK();
+    }
+    return SFA_OK;
+}
+
+static unsigned zgrid(long long tiles) { return (unsigned)(tiles < 65535LL * 16 ? tiles : 65535LL * 16); }
+
+// Bins [0, nf) of d / X / out (pointers already offset to the first bin); nf <= p.fc.
+static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, const double2* yl, const double2* dd,
+                        const void* X, void* out, unsigned char* w, cudaStream_t st) {
+    const long long L = s->L, Q = s->Q, T = s->T;
+    const int M = s->M, Cd = s->Cd;
+    const bool c64 = s->precision == SFA_PREC_C64_3XTF32;
+    const long long LQ = L * p.Qp;
+    int rc;
+    if (c64) {
+        const float2* x = reinterpret_cast<const float2*>(X);
+        float2* o = reinterpret_cast<float2*>(out);
+        if (p.form == 1) {
+            const float2* G = reinterpret_cast<const float2*>(w + p.off_G);
+            float* A = reinterpret_cast<float*>(w + p.off_A);
+            for (long long g0 = 0; g0 < nf; g0 += 64) {          // d staged through smem, <= 64 bins a time
+                const int ng = (int)((nf - g0 < 64) ? nf - g0 : 64);
+                steer_build_split_kernel<<<grid1d(LQ), 256, (size_t)ng * Cd * sizeof(float2), st>>>(
+                    G, dd, Cd, Cd, g0, ng, LQ, A + g0 * 4 * LQ);
+                SFA_LAUNCH_CHECK();
+            }
+            return cgemm_splitk(nf, L, T, Q, A, p.Qp, 0, x, T, Q * T, o, T, L * T, nullptr, 0, st);
+        }
+        const float* P1 = reinterpret_cast<const float*>(w + p.off_P1);
+        const float* P2 = reinterpret_cast<const float*>(w + p.off_P2);
+        float2* dcols = reinterpret_cast<float2*>(w + p.off_dcols);
+        float2* Z = reinterpret_cast<float2*>(w + p.off_Z);
+        expand_diag_kernel<float2><<<grid1d(nf * M), 256, 0, st>>>(dd, nf, Cd, M, s->d_is_per_order, dcols);
+        SFA_LAUNCH_CHECK();
+        rc = cgemm_splitk(nf, M, T, Q, P1, p.Qp, 1, x, T, Q * T, Z, p.Tld, (long long)M * p.Tld, dcols, M, st);
+        if (rc != SFA_OK) return rc;
+        return cgemm_splitk(nf, L, T, M, P2, p.Mp, 1, Z, p.Tld, (long long)M * p.Tld, o, T, L * T, nullptr, 0, st);
+    }
+    const double2* x = reinterpret_cast<const double2*>(X);
+    double2* o = reinterpret_cast<double2*>(out);
+    if (p.form == 1) {
+        const double2* G = reinterpret_cast<const double2*>(w + p.off_G);
+        double2* A = reinterpret_cast<double2*>(w + p.off_A);
+        steer_build_f64_kernel<<<grid1d(LQ * nf), 256, 0, st>>>(G, dd, Cd, Cd, 0, (int)nf, LQ, A);
+        SFA_LAUNCH_CHECK();
+        zgemm_kernel<<<zgrid(nf * ceil_div(T, 64) * ceil_div(L, 64)), 256, 0, st>>>(
+            nf, L, T, Q, A, p.Qp, LQ, x, T, Q * T, o, T, L * T, nullptr, 0);
+        SFA_LAUNCH_CHECK();
+        return SFA_OK;
+    }
+    const double2* P1 = reinterpret_cast<const double2*>(w + p.off_P1);      // conj(Y_Q)^T [M][Q]
+    double2* dcols = reinterpret_cast<double2*>(w + p.off_dcols);
+    double2* Z = reinterpret_cast<double2*>(w + p.off_Z);
+    expand_diag_kernel<double2><<<grid1d(nf * M), 256, 0, st>>>(dd, nf, Cd, M, s->d_is_per_order, dcols);
+    SFA_LAUNCH_CHECK();
+    zgemm_kernel<<<zgrid(nf * ceil_div(T, 64) * ceil_div(M, 64)), 256, 0, st>>>(
+        nf, M, T, Q, P1, Q, 0, x, T, Q * T, Z, p.Tld, (long long)M * p.Tld, dcols, M);
+    SFA_LAUNCH_CHECK();
+    zgemm_kernel<<<zgrid(nf * ceil_div(T, 64) * ceil_div(L, 64)), 256, 0, st>>>(
+        nf, L, T, M, yl, M, 0, Z, p.Tld, (long long)M * p.Tld, o, T, L * T, nullptr, 0);
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+static inline size_t elem_bytes(const sfa_pwd_shape* s) { return s->precision == SFA_PREC_C64_3XTF32 ? 8 : 16; }
+
+}  // namespace sfa
+
+using namespace sfa;
+
+extern "C" size_t sfa_pwd_work_bytes(const sfa_pwd_shape* s) {
+    Plan p;
+    if (make_plan(s, &p) != SFA_OK) return 0;
+    return p.total;
+}
+
+extern "C" int sfa_pwd_apply(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* Y_Q,
+                             const sfa_c128* d, const void* X, void* out, void* work, size_t work_bytes,
+                             void* stream) {
+    Plan p;
+    int rc = make_plan(s, &p);
+    if (rc != SFA_OK) return rc;
+    if (s->F == 0) return SFA_OK;
+    if (!Y_L || !Y_Q || !d || !X || !out || !work) return SFA_ERR_INVALID;
+    if (work_bytes < p.total) return SFA_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
+    const double2* yl = reinterpret_cast<const double2*>(Y_L);
+    const double2* dd = reinterpret_cast<const double2*>(d);
+    rc = pwd_prepare(s, p, yl, reinterpret_cast<const double2*>(Y_Q), w, st);
+    if (rc != SFA_OK) return rc;
+    const size_t eb = elem_bytes(s);
+    for (long long f0 = 0; f0 < s->F; f0 += p.fc) {
+        const long long nf = (s->F - f0 < p.fc) ? (s->F - f0) : p.fc;
+        rc = pwd_run_bins(s, p, nf, yl, dd + f0 * s->Cd,
+                          reinterpret_cast<const unsigned char*>(X) + (size_t)f0 * s->Q * s->T * eb,
+                          reinterpret_cast<unsigned char*>(out) + (size_t)f0 * s->L * s->T * eb, w, st);
+        if (rc != SFA_OK) return rc;
+    }
+    return SFA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Host-buffer path: chunked H2D -> compute -> D2H pipeline on three streams.
+// ---------------------------------------------------------------------------
+struct sfa_pwd_host_ctx {
+    sfa_pwd_shape shape;
+    Plan plan;
+    int device;
+    long long chunk;                 // bins per pipeline slot (multiple of plan.fc)
+    cudaStream_t s_in, s_cmp, s_out;
+    cudaEvent_t in_done[2], cmp_done[2], out_done[2];
+    unsigned char *d_YL, *d_YQ, *d_d, *d_work, *d_X[2], *d_O[2];
+    bool operators_set;
+};
+
+extern "C" int sfa_pwd_host_create(sfa_pwd_host_ctx** out_ctx, const sfa_pwd_shape* s, int device,
+                                   int64_t chunk_bins) {
+    if (!out_ctx || !s) return SFA_ERR_INVALID;
+    SFA_CUDA_CHECK(cudaSetDevice(device));
+    sfa_pwd_host_ctx* c = new sfa_pwd_host_ctx();
+    c->shape = *s;
+    int rc = make_plan(s, &c->plan);
+    if (rc != SFA_OK) {
+        delete c;
+        return rc;
+    }
+    c->device = device;
+    long long chunk = chunk_bins > 0 ? chunk_bins : c->plan.fc;
+    if (chunk > s->F) chunk = s->F > 0 ? s->F : 1;
+    c->chunk = chunk;
+    c->operators_set = false;
+    const size_t eb = elem_bytes(s);
+    SFA_CUDA_CHECK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    SFA_CUDA_CHECK(cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking));
+    SFA_CUDA_CHECK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        SFA_CUDA_CHECK(cudaEventCreateWithFlags(&c->in_done[i], cudaEventDisableTiming));
+        SFA_CUDA_CHECK(cudaEventCreateWithFlags(&c->cmp_done[i], cudaEventDisableTiming));
+        SFA_CUDA_CHECK(cudaEventCreateWithFlags(&c->out_done[i], cudaEventDisableTiming));
+        SFA_CUDA_CHECK(cudaMalloc(&c->d_X[i], (size_t)chunk * s->Q * s->T * eb));
+        SFA_CUDA_CHECK(cudaMalloc(&c->d_O[i], (size_t)chunk * s->L * s->T * eb));
+    }
+    SFA_CUDA_CHECK(cudaMalloc(&c->d_YL, (size_t)s->L * s->M * 16));
+    SFA_CUDA_CHECK(cudaMalloc(&c->d_YQ, (size_t)s->Q * s->M * 16));
+    SFA_CUDA_CHECK(cudaMalloc(&c->d_d, (size_t)(s->F > 0 ? s->F : 1) * s->Cd * 16));
+    SFA_CUDA_CHECK(cudaMalloc(&c->d_work, c->plan.total));
+    *out_ctx = c;
+    return SFA_OK;
+}
+
+extern "C" int sfa_pwd_host_set_operators(sfa_pwd_host_ctx* c, const sfa_c128* Y_L, const sfa_c128* Y_Q,
+                                          const sfa_c128* d) {
+    if (!c || !Y_L || !Y_Q || !d) return SFA_ERR_INVALID;
+    const sfa_pwd_shape* s = &c->shape;
+    SFA_CUDA_CHECK(cudaSetDevice(c->device));
+    SFA_CUDA_CHECK(cudaMemcpyAsync(c->d_YL, Y_L, (size_t)s->L * s->M * 16, cudaMemcpyHostToDevice, c->s_cmp));
+    SFA_CUDA_CHECK(cudaMemcpyAsync(c->d_YQ, Y_Q, (size_t)s->Q * s->M * 16, cudaMemcpyHostToDevice, c->s_cmp));
+    SFA_CUDA_CHECK(cudaMemcpyAsync(c->d_d, d, (size_t)s->F * s->Cd * 16, cudaMemcpyHostToDevice, c->s_cmp));
+    unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)c->d_work + 255) & ~(uintptr_t)255);
+    int rc = pwd_prepare(s, c->plan, reinterpret_cast<const double2*>(c->d_YL),
+                         reinterpret_cast<const double2*>(c->d_YQ), w, c->s_cmp);
+    if (rc != SFA_OK) return rc;
+    SFA_CUDA_CHECK(cudaStreamSynchronize(c->s_cmp));
+    c->operators_set = true;
+    return SFA_OK;
+}
+
+extern "C" int sfa_pwd_host_run(sfa_pwd_host_ctx* c, const void* X_host, void* out_host) {
+    if (!c || !X_host || !out_host || !c->operators_set) return SFA_ERR_INVALID;
+    const sfa_pwd_shape* s = &c->shape;
+    SFA_CUDA_CHECK(cudaSetDevice(c->device));
+    const size_t eb = elem_bytes(s);
+    unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)c->d_work + 255) & ~(uintptr_t)255);
+    const size_t x_bin = (size_t)s->Q * s->T * eb, o_bin = (size_t)s->L * s->T * eb;
+    int slot = 0;
+    long long it = 0;
+    for (long long f0 = 0; f0 < s->F; f0 += c->chunk, ++it, slot ^= 1) {
+        const long long nf = (s->F - f0 < c->chunk) ? (s->F - f0) : c->chunk;
+        // the input slot is free once the compute that read it (two chunks ago) has finished
+        if (it >= 2) SFA_CUDA_CHECK(cudaStreamWaitEvent(c->s_in, c->cmp_done[slot], 0));
+        SFA_CUDA_CHECK(cudaMemcpyAsync(c->d_X[slot], reinterpret_cast<const unsigned char*>(X_host) + f0 * x_bin,
+                                       nf * x_bin, cudaMemcpyHostToDevice, c->s_in));
+        SFA_CUDA_CHECK(cudaEventRecord(c->in_done[slot], c->s_in));
+        SFA_CUDA_CHECK(cudaStreamWaitEvent(c->s_cmp, c->in_done[slot], 0));
+        // the output slot is free once its previous contents have been copied out
+        if (it >= 2) SFA_CUDA_CHECK(cudaStreamWaitEvent(c->s_cmp, c->out_done[slot], 0));
+        for (long long g0 = 0; g0 < nf; g0 += c->plan.fc) {
+            const long long ng = (nf - g0 < c->plan.fc) ? (nf - g0) : c->plan.fc;
+            int rc = pwd_run_bins(s, c->plan, ng, reinterpret_cast<const double2*>(c->d_YL),
+                                  reinterpret_cast<const double2*>(c->d_d) + (f0 + g0) * s->Cd,
+                                  c->d_X[slot] + g0 * x_bin, c->d_O[slot] + g0 * o_bin, w, c->s_cmp);
+            if (rc != SFA_OK) return rc;
+        }
+        SFA_CUDA_CHECK(cudaEventRecord(c->cmp_done[slot], c->s_cmp));
+        SFA_CUDA_CHECK(cudaStreamWaitEvent(c->s_out, c->cmp_done[slot], 0));
+        SFA_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(out_host) + f0 * o_bin, c->d_O[slot],
+                                       nf * o_bin, cudaMemcpyDeviceToHost, c->s_out));
+        SFA_CUDA_CHECK(cudaEventRecord(c->out_done[slot], c->s_out));
+    }
+    SFA_CUDA_CHECK(cudaStreamSynchronize(c->s_out));
+    SFA_CUDA_CHECK(cudaStreamSynchronize(c->s_cmp));
+    return SFA_OK;
+}
+
+extern "C" int sfa_pwd_host_destroy(sfa_pwd_host_ctx* c) {
+    if (!c) return SFA_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->d_X[i]);
+        cudaFree(c->d_O[i]);
+        cudaEventDestroy(c->in_done[i]);
+        cudaEventDestroy(c->cmp_done[i]);
+        cudaEventDestroy(c->out_done[i]);
+    }
+    cudaFree(c->d_YL);
+    cudaFree(c->d_YQ);
+    cudaFree(c->d_d);
+    cudaFree(c->d_work);
+    cudaStreamDestroy(c->s_in);
+    cudaStreamDestroy(c->s_cmp);
+    cudaStreamDestroy(c->s_out);
+    delete c;
+    return SFA_OK;
+}
+
+// Test/bench entry: raw complex64 operands; P is split into planes in `scratch`-free fashion by
+// allocating a temporary (stream-ordered) buffer.
+extern "C" int sfa_cgemm3x(int64_t B, int64_t Nn, int64_t Mm, int64_t K, const sfa_c64* P, int64_t ldP,
+                           int64_t strideP, const sfa_c64* R, int64_t ldR, int64_t strideR, sfa_c64* out,
+                           int64_t ldo, int64_t strideO, const sfa_c64* rowscale, int64_t strideS,
+                           void* stream);
+
+namespace sfa {
+__global__ void split_planar_c64_kernel(const float2* __restrict__ S, long long ld, long long strideB,
+                                        long long batches, long long Nn, long long K, long long Kp,
+                                        float* __restrict__ P) {
+    const long long plane = Nn * Kp;
+    const long long total = batches * plane;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / plane, r = i - b * plane;
+        const long long n = r / Kp, k = r - n * Kp;
+        float2 v = make_float2(0.f, 0.f);
+        if (k < K) v = S[b * strideB + n * ld + k];
+        float* o = P + b * 4 * plane + r;
+        const float hr = __uint_as_float(tf32_rna(v.x)), hi = __uint_as_float(tf32_rna(v.y));
+        o[0] = hr;
+        o[plane] = hi;
+        o[2 * plane] = v.x - hr;
+        o[3 * plane] = v.y - hi;
+    }
+}
+}  // namespace sfa
+
+extern "C" int sfa_cgemm3x(int64_t B, int64_t Nn, int64_t Mm, int64_t K, const sfa_c64* P, int64_t ldP,
+                           int64_t strideP, const sfa_c64* R, int64_t ldR, int64_t strideR, sfa_c64* out,
+                           int64_t ldo, int64_t strideO, const sfa_c64* rowscale, int64_t strideS,
+                           void* stream) {
+    if (B < 0 || Nn < 0 || Mm < 0 || K <= 0) return SFA_ERR_INVALID;
+    if (B == 0 || Nn == 0 || Mm == 0) return SFA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long Kp = round_up(K, 4);
+    const long long pb = strideP == 0 ? 1 : B;
+    float* Pp = nullptr;
+    SFA_CUDA_CHECK(cudaMallocAsync(&Pp, (size_t)pb * 4 * Nn * Kp * sizeof(float), st));
+    split_planar_c64_kernel<<<grid1d(pb * Nn * Kp), 256, 0, st>>>(reinterpret_cast<const float2*>(P), ldP, strideP,
+                                                                   pb, Nn, K, Kp, Pp);
+    int rc = SFA_OK;
+    if (cudaGetLastError() != cudaSuccess) rc = SFA_ERR_CUDA;
+    if (rc == SFA_OK)
+        rc = cgemm_splitk(B, Nn, Mm, K, Pp, Kp, strideP == 0, reinterpret_cast<const float2*>(R), ldR, strideR,
+                          reinterpret_cast<float2*>(out), ldo, strideO, reinterpret_cast<const float2*>(rowscale),
+                          strideS, st);
+    cudaFreeAsync(Pp, st);
+    return rc;
+}

@@ -1,0 +1,344 @@
+// Stage 2: radial mode strengths b_n(kr), zero replacement, regularised inverse.
+//
+//   sfa_radial_filter  <- radial.weights / spherical_pw / spherical_ps            radial.py:36-162
+//                         radial.circ_radial_weights / circular_pw / circular_ls  radial.py:317-441
+//                         + replace_zeros_of_radial_function (decorator)          radial.py:9-33,165-213
+//                         + regularize(1/bn, a0, method)                          radial.py:216-266
+//   sfa_regularize, sfa_replace_zeros, sfa_repeat_n_m, sfa_diagonal_stack         radial.py:216-314,444-465
+//
+// radial_filter_kernel: one thread per wavenumber runs the FP64 recurrences of
+// sfa_math.cuh (Miller backward for j_n/J_n, forward for y_n/Y_n) with its
+// scratch arrays strided through shared memory (conflict-free), writes its row
+// into a shared tile, and the CTA then streams the tile out with coalesced
+// 16-byte stores -- b_n, and in the same pass d_n = (1/b_n) h_n and h_n, so the
+// inverse never makes a separate trip through HBM.  Algorithmic traffic: 8 B in
+// per bin, 16 B per b_n out (+16 +8/16 B per (d_n, h_n)).
+#include "sfa_common.cuh"
+#include "sfa_math.cuh"
+
+namespace sfa {
+
+constexpr double kZeroThreshold = 1e-300;    // radial.py:198
+constexpr int kRadialThreads = 128;
+constexpr long long kWorklistCap = 1 << 20;  // zero entries that can be repaired per call
+
+struct TileOut {
+    double2* row;
+    __device__ __forceinline__ void operator()(int c, c128 v) const { row[c] = make_double2(v.re, v.im); }
+};
+
+__device__ __forceinline__ bool is_zero_entry(double2 v) { return hypot(v.x, v.y) < kZeroThreshold; }
+
+// status[0] zero count, [1] unrepairable column, [2] worklist overflow, [3] worklist length
+__global__ void __launch_bounds__(kRadialThreads)
+radial_filter_kernel(int family, int N, long long F, const double* __restrict__ k, double r, double rs,
+                     int setup, int scale, int want_zero_list, int method, double a0, double alpha,
+                     double2* __restrict__ bn, double2* __restrict__ dn, double* __restrict__ hn_real,
+                     double2* __restrict__ hn_cplx, int* __restrict__ status,
+                     long long* __restrict__ worklist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int C = family ? 2 * N + 1 : N + 1;
+    const int Cp = C | 1;                                   // odd row pitch: conflict-free 16 B rows
+    const int T = blockDim.x;
+    double2* tile = reinterpret_cast<double2*>(smem_raw);   // [T][Cp]
+    double* scratch = reinterpret_cast<double*>(tile + (size_t)T * Cp);   // 2 arrays [(N+3)][T]
+    const int tid = threadIdx.x;
+    const long long nblk = (F + T - 1) / T;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const long long f0 = blk * T;
+        const long long f = f0 + tid;
+        if (f < F) {
+            dvec jx{scratch + tid, T};
+            dvec js{scratch + (size_t)(N + 3) * T + tid, T};
+            TileOut out{tile + (size_t)tid * Cp};
+            if (family == 0) sph_radial_row(N, k[f], r, rs, setup, scale, jx, js, out);
+            else circ_radial_row(N, k[f], r, rs, setup, scale, jx, js, out);
+        }
+        __syncthreads();
+        const int rows = (int)((F - f0 < T) ? (F - f0) : T);
+        const int total = rows * C;
+        int local_zero = 0;
+        for (int e = tid; e < total; e += T) {
+            const int rr = e / C, cc = e - rr * C;
+            const double2 b = tile[(size_t)rr * Cp + cc];
+            const long long g = f0 * C + e;
+            bn[g] = b;
+            if (is_zero_entry(b)) {
+                ++local_zero;
+                if (want_zero_list) {
+                    const int slot = atomicAdd(&status[3], 1);
+                    if (slot < kWorklistCap) worklist[slot] = g;
+                    else status[2] = 1;
+                }
+            }
+            if (method >= 0) {
+                c128 d;
+                double h;
+                regularize_one(cdiv(mk(1.0, 0.0), mk(b.x, b.y)), a0, method, alpha, &d, &h);
+                dn[g] = make_double2(d.re, d.im);
+                if (hn_real) hn_real[g] = h;
+                else hn_cplx[g] = make_double2(h, 0.0);
+            }
+        }
+        if (local_zero) atomicAdd(&status[0], local_zero);
+        __syncthreads();
+    }
+}
+
+// Phase 1 of the repair: for every listed zero entry find the row of the nearest
+// kr whose entry in the same column is non-zero (ties -> smaller kr, which is what
+// argmin over the kr-sorted rows gives, radial.py:200-206).  One warp per entry.
+// `order` maps sorted position -> row (NULL: rows are already sorted by kr).
+__global__ void find_replacement_kernel(long long F, int C, const double* __restrict__ kr,
+                                        const double2* __restrict__ A, int* __restrict__ status,
+                                        long long* __restrict__ worklist) {
+    const int nlist = min((long long)status[3], kWorklistCap);
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long e = warp; e < nlist; e += nwarps) {
+        const long long g = worklist[e];
+        const long long i = g / C;
+        const int j = (int)(g - i * C);
+        const double ki = kr[i];
+        double best = INFINITY, bestk = INFINITY;
+        long long besti = -1;
+        for (long long l = lane; l < F; l += 32) {
+            if (is_zero_entry(A[l * C + j])) continue;
+            const double dist = fabs(kr[l] - ki);
+            const double kl = kr[l];
+            if (dist < best || (dist == best && (kl < bestk || (kl == bestk && l < besti)))) {
+                best = dist;
+                bestk = kl;
+                besti = l;
+            }
+        }
+        for (int off = 16; off; off >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const double ok = __shfl_xor_sync(0xffffffffu, bestk, off);
+            const long long oi = __shfl_xor_sync(0xffffffffu, besti, off);
+            const bool take = (oi >= 0) && (besti < 0 || ob < best ||
+                              (ob == best && (ok < bestk || (ok == bestk && oi < besti))));
+            if (take) {
+                best = ob;
+                bestk = ok;
+                besti = oi;
+            }
+        }
+        if (lane == 0) {
+            if (besti < 0) status[1] = 1;
+            worklist[kWorklistCap + e] = besti;
+        }
+    }
+}
+
+// Phase 2: copy the replacement values and redo the inverse at those entries.
+__global__ void apply_replacement_kernel(int C, int method, double a0, double alpha,
+                                         double2* __restrict__ A, double2* __restrict__ dn,
+                                         double* __restrict__ hn_real, double2* __restrict__ hn_cplx,
+                                         const int* __restrict__ status,
+                                         const long long* __restrict__ worklist) {
+    const int nlist = min((long long)status[3], kWorklistCap);
+    if (status[1]) return;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nlist;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long g = worklist[e];
+        const long long src = worklist[kWorklistCap + e];
+        if (src < 0) continue;
+        const int j = (int)(g % C);
+        const double2 b = A[src * C + j];
+        A[g] = b;
+        if (method >= 0) {
+            c128 d;
+            double h;
+            regularize_one(cdiv(mk(1.0, 0.0), mk(b.x, b.y)), a0, method, alpha, &d, &h);
+            dn[g] = make_double2(d.re, d.im);
+            if (hn_real) hn_real[g] = h;
+            else hn_cplx[g] = make_double2(h, 0.0);
+        }
+    }
+}
+
+// Lists the zero entries of an existing matrix (standalone replace_zeros path).
+__global__ void list_zeros_kernel(long long total, const double2* __restrict__ A,
+                                  int* __restrict__ status, long long* __restrict__ worklist) {
+    int local = 0;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        if (is_zero_entry(A[g])) {
+            ++local;
+            const int slot = atomicAdd(&status[3], 1);
+            if (slot < kWorklistCap) worklist[slot] = g;
+            else status[2] = 1;
+        }
+    }
+    if (local) atomicAdd(&status[0], local);
+}
+
+__global__ void regularize_kernel(long long n, const double2* __restrict__ in, double a0, int method,
+                                  double alpha, double2* __restrict__ out, double* __restrict__ hn_real,
+                                  double2* __restrict__ hn_cplx) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const double2 v = in[i];
+        c128 d;
+        double h;
+        regularize_one(mk(v.x, v.y), a0, method, alpha, &d, &h);
+        out[i] = make_double2(d.re, d.im);
+        if (hn_real) hn_real[i] = h;
+        else if (hn_cplx) hn_cplx[i] = make_double2(h, 0.0);
+    }
+}
+
+__global__ void repeat_n_m_kernel(long long F, int N, const double2* __restrict__ v,
+                                  double2* __restrict__ out) {
+    const int M = (N + 1) * (N + 1);
+    const long long total = F * M;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const long long f = g / M;
+        const int i = (int)(g - f * M);
+        int n = (int)sqrtf((float)i);
+        while ((n + 1) * (n + 1) <= i) ++n;
+        while (n * n > i) --n;
+        out[g] = v[f * (N + 1) + n];
+    }
+}
+
+__global__ void diagonal_stack_kernel(long long F, int M, const double2* __restrict__ d,
+                                      double2* __restrict__ D) {
+    const long long per = (long long)M * M;
+    const long long total = F * per;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const long long f = g / per;
+        const long long rem = g - f * per;
+        const int i = (int)(rem / M), j = (int)(rem - (long long)i * M);
+        D[g] = (i == j) ? d[f * M + i] : make_double2(0.0, 0.0);
+    }
+}
+
+static unsigned grid_for(long long items, int threads) {
+    long long blocks = ceil_div(items, threads);
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+static void split_hn(int method, void* hn, double** hr, double2** hc) {
+    *hr = nullptr;
+    *hc = nullptr;
+    if (method < 0 || !hn) return;
+    if (method <= REG_HARDCLIP) *hc = reinterpret_cast<double2*>(hn);
+    else *hr = reinterpret_cast<double*>(hn);
+}
+
+}  // namespace sfa
+
+using namespace sfa;
+
+extern "C" size_t sfa_radial_work_bytes(int, int, int64_t) {
+    return (size_t)(2 * kWorklistCap) * sizeof(long long);
+}
+
+extern "C" int sfa_radial_filter(int kind, int N, int64_t F, const double* k, double r, double rs,
+                                 int setup, int replace_zeros, int method, double a0,
+                                 sfa_c128* bn, sfa_c128* dn, void* hn, int32_t* status, void* work,
+                                 void* stream) {
+    if (kind < 0 || kind > SFA_CIRC_LS || N < 0 || F < 0 || setup < 0 || setup > SFA_RIGID ||
+        method > SFA_REG_WNG || !status)
+        return SFA_ERR_INVALID;
+    if (F > 0 && (!k || !bn)) return SFA_ERR_INVALID;
+    if (method >= 0 && (!dn || !hn)) return SFA_ERR_INVALID;
+    if (replace_zeros && !work) return SFA_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    SFA_CUDA_CHECK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
+    if (F == 0) return SFA_OK;
+    const int family = kind >= SFA_CIRC_WEIGHTS;
+    const int scale = family ? kind - SFA_CIRC_WEIGHTS : kind;
+    const int C = family ? 2 * N + 1 : N + 1;
+    const int Cp = C | 1;
+    const int T = kRadialThreads;
+    const size_t smem = (size_t)T * Cp * sizeof(double2) + (size_t)2 * (N + 3) * T * sizeof(double);
+    if (smem > 220 * 1024) return SFA_ERR_UNSUPPORTED;
+    SFA_CUDA_CHECK(cudaFuncSetAttribute(radial_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const double alpha = (method == SFA_REG_TIKH) ? tikh_alpha(a0) : 0.0;
+    double* hr;
+    double2* hc;
+    split_hn(method, hn, &hr, &hc);
+    long long blocks = ceil_div(F, T);
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    long long* wl = reinterpret_cast<long long*>(work);
+    radial_filter_kernel<<<(unsigned)blocks, T, smem, st>>>(
+        family, N, F, k, r, rs, setup, scale, replace_zeros ? 1 : 0, method, a0, alpha,
+        reinterpret_cast<double2*>(bn), reinterpret_cast<double2*>(dn), hr, hc, status, wl);
+    SFA_LAUNCH_CHECK();
+    if (replace_zeros) {
+        // Both kernels return at once when the zero list is empty (the normal case).
+        find_replacement_kernel<<<64, 256, 0, st>>>(F, C, k, reinterpret_cast<double2*>(bn), status, wl);
+        SFA_LAUNCH_CHECK();
+        apply_replacement_kernel<<<32, 256, 0, st>>>(C, method, a0, alpha, reinterpret_cast<double2*>(bn),
+                                                      reinterpret_cast<double2*>(dn), hr, hc, status, wl);
+        SFA_LAUNCH_CHECK();
+    }
+    return SFA_OK;
+}
+
+extern "C" int sfa_replace_zeros(int64_t F, int C, const double* kr_sorted, sfa_c128* A,
+                                 int32_t* status, void* work, size_t work_bytes, void* stream) {
+    if (F < 0 || C < 0 || !status || !work) return SFA_ERR_INVALID;
+    if (work_bytes < sfa_radial_work_bytes(0, 0, F)) return SFA_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    SFA_CUDA_CHECK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
+    if (F == 0 || C == 0) return SFA_OK;
+    if (!kr_sorted || !A) return SFA_ERR_INVALID;
+    long long* wl = reinterpret_cast<long long*>(work);
+    double2* a = reinterpret_cast<double2*>(A);
+    list_zeros_kernel<<<grid_for((long long)F * C, 256), 256, 0, st>>>((long long)F * C, a, status, wl);
+    SFA_LAUNCH_CHECK();
+    find_replacement_kernel<<<64, 256, 0, st>>>(F, C, kr_sorted, a, status, wl);
+    SFA_LAUNCH_CHECK();
+    apply_replacement_kernel<<<32, 256, 0, st>>>(C, -1, 0.0, 0.0, a, nullptr, nullptr, nullptr, status, wl);
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+extern "C" int sfa_regularize(int64_t n, const sfa_c128* dn_in, double a0, int method,
+                              sfa_c128* dn_out, void* hn, void* stream) {
+    if (n < 0 || method < 0 || method > SFA_REG_WNG) return SFA_ERR_INVALID;
+    if (n == 0) return SFA_OK;
+    if (!dn_in || !dn_out) return SFA_ERR_INVALID;
+    double* hr;
+    double2* hc;
+    split_hn(method, hn, &hr, &hc);
+    const double alpha = (method == SFA_REG_TIKH) ? tikh_alpha(a0) : 0.0;
+    regularize_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        n, reinterpret_cast<const double2*>(dn_in), a0, method, alpha,
+        reinterpret_cast<double2*>(dn_out), hr, hc);
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+extern "C" int sfa_repeat_n_m(int64_t F, int N, const sfa_c128* v, sfa_c128* out, void* stream) {
+    if (F < 0 || N < 0) return SFA_ERR_INVALID;
+    if (F == 0) return SFA_OK;
+    if (!v || !out) return SFA_ERR_INVALID;
+    const long long total = (long long)F * (N + 1) * (N + 1);
+    repeat_n_m_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        F, N, reinterpret_cast<const double2*>(v), reinterpret_cast<double2*>(out));
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+extern "C" int sfa_diagonal_stack(int64_t F, int M, const sfa_c128* d, sfa_c128* D, void* stream) {
+    if (F < 0 || M < 0) return SFA_ERR_INVALID;
+    if (F == 0 || M == 0) return SFA_OK;
+    if (!d || !D) return SFA_ERR_INVALID;
+    const long long total = (long long)F * M * M;
+    diagonal_stack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        F, M, reinterpret_cast<const double2*>(d), reinterpret_cast<double2*>(D));
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}

@@ -1,0 +1,190 @@
+"""Plane-wave decomposition / steering: ``q_f = Y_L diag(d_f) Y_Q^H X_f`` for every bin.
+
+The reference has no function for this step -- every example script spells it
+as a dense diagonal stack and three ``np.matmul`` calls
+(doc/examples/modal_beamforming_rigid_spherical_array.py:36-39):
+
+    D = diagonal_mode_mat(dn)
+    A = np.matmul(np.matmul(Y_q, D), np.conj(Y_p.T))
+    q = np.matmul(A, p[:, :, None])
+
+``pwd(Y_q, dn, Y_p, p)`` computes exactly that ``q`` (same argument roles)
+without ever forming ``D`` ([F, M, M]) or, at large sizes, ``A`` ([F, L, Q]).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..util import as_complex_tensor, _device_of
+
+PRECISIONS = {"c64": 0, "c128": 1}
+FORMS = {"auto": 0, "steering": 1, "factored": 2}
+
+
+def _shape_of(Y_look, dn, Y_mic, F, Q, T, precision, form):
+    L, M = Y_look.shape
+    if Y_mic.shape != (Q, M):
+        raise ValueError("Y_mic must have shape (Q, M) = ({}, {}), got {}".format(Q, M, tuple(Y_mic.shape)))
+    if dn.shape[0] != F:
+        raise ValueError("dn must have one row per frequency bin ({}), got {}".format(F, dn.shape[0]))
+    Cd = dn.shape[1]
+    if Cd == M:
+        per_order = 0
+    elif Cd * Cd == M:
+        per_order = 1                      # radial.diagonal_mode_mat semantics (repeat_n_m, radial.py:284)
+    else:
+        raise ValueError("dn has {} columns; expected M={} (per column) or sqrt(M) (per order)".format(Cd, M))
+    return _lib.PwdShape(F, L, Q, T, M, Cd, per_order, PRECISIONS[precision], FORMS[form])
+
+
+def pwd(Y_look, dn, Y_mic, p, precision=None, form="auto", out=None):
+    """Apply the modal beamformer to microphone spectra.
+
+    Parameters
+    ----------
+    Y_look : (L, M) SH/CH matrix at the look directions (``Y_q`` in the examples).
+    dn : (F, N+1) radial filters per order (spherical, expanded like ``diagonal_mode_mat``),
+         or (F, M) per column (circular: ``circ_diagonal_mode_mat``).
+    Y_mic : (Q, M) SH/CH matrix at the microphones, already carrying the quadrature
+         weights (``Y_p`` in the examples); it enters conjugate-transposed.
+    p : (F, Q) or (F, Q, T) microphone spectra.
+    precision : "c64" (tensor cores, 3xTF32, FP32 accumulate; error ~1e-6 normwise) or
+         "c128" (FP64).  Default: from ``p``'s dtype (complex64 -> "c64", else "c128").
+    Returns
+    -------
+    q : (F, L, T) beam outputs (``np.matmul(A, p[:, :, None])`` keeps the T axis, so T=1 for 2-D p).
+    """
+    lib = _lib.require_cuda()
+    dev = _device_of(p, Y_look, dn, Y_mic)
+    if precision is None:
+        pd = p.dtype if isinstance(p, torch.Tensor) else np.asarray(p).dtype
+        precision = "c64" if pd in (torch.complex64, np.complex64) else "c128"
+    if precision not in PRECISIONS:
+        raise ValueError("precision must be 'c64' or 'c128'")
+    if form not in FORMS:
+        raise ValueError("form must be 'auto', 'steering' or 'factored'")
+    cdtype = torch.complex64 if precision == "c64" else torch.complex128
+    Y_look = as_complex_tensor(Y_look, dev)
+    Y_mic = as_complex_tensor(Y_mic, dev)
+    dn = as_complex_tensor(dn, dev)
+    if dn.ndim == 1:
+        dn = dn[None, :]
+    X = as_complex_tensor(p, dev, cdtype)
+    if X.ndim == 2:
+        X = X[:, :, None]
+    if X.ndim != 3:
+        raise ValueError("p must have shape (F, Q) or (F, Q, T)")
+    F, Q, T = X.shape
+    shape = _shape_of(Y_look, dn, Y_mic, F, Q, T, precision, form)
+    L = Y_look.shape[0]
+    if out is None:
+        out = torch.empty((F, L, T), dtype=cdtype, device=dev)
+    elif out.shape != (F, L, T) or out.dtype != cdtype or not out.is_contiguous() or out.device != dev:
+        raise ValueError("out must be a contiguous {} tensor of shape {}".format(cdtype, (F, L, T)))
+    nbytes = lib.sfa_pwd_work_bytes(ctypes.byref(shape))
+    if nbytes == 0:
+        raise ValueError("unsupported plane-wave-decomposition shape")
+    work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sfa_pwd_apply(ctypes.byref(shape), _lib.ptr(Y_look), _lib.ptr(Y_mic), _lib.ptr(dn),
+                                     _lib.ptr(X), _lib.ptr(out), _lib.ptr(work), nbytes, _lib.stream_ptr(dev)))
+    return out
+
+
+class PwdPlan:
+    """Reusable device-side plan: workspace allocated once, operators kept resident."""
+
+    def __init__(self, Y_look, dn, Y_mic, T, precision="c64", form="auto", device=None):
+        self.lib = _lib.require_cuda()
+        dev = device if device is not None else _device_of(Y_look, dn, Y_mic)
+        self.dev = dev
+        self.cdtype = torch.complex64 if precision == "c64" else torch.complex128
+        self.Y_look = as_complex_tensor(Y_look, dev)
+        self.Y_mic = as_complex_tensor(Y_mic, dev)
+        dn = as_complex_tensor(dn, dev)
+        self.dn = dn[None, :] if dn.ndim == 1 else dn
+        F, Q = self.dn.shape[0], self.Y_mic.shape[0]
+        self.shape = _shape_of(self.Y_look, self.dn, self.Y_mic, F, Q, int(T), precision, form)
+        self.nbytes = self.lib.sfa_pwd_work_bytes(ctypes.byref(self.shape))
+        if self.nbytes == 0:
+            raise ValueError("unsupported plane-wave-decomposition shape")
+        self.work = torch.empty(self.nbytes, dtype=torch.uint8, device=dev)
+        self.out_shape = (F, self.Y_look.shape[0], int(T))
+
+    def __call__(self, X, out=None):
+        if X.dtype != self.cdtype or not X.is_contiguous() or X.device != self.dev:
+            raise ValueError("X must be a contiguous {} tensor on {}".format(self.cdtype, self.dev))
+        if out is None:
+            out = torch.empty(self.out_shape, dtype=self.cdtype, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.sfa_pwd_apply(ctypes.byref(self.shape), _lib.ptr(self.Y_look), _lib.ptr(self.Y_mic),
+                                              _lib.ptr(self.dn), _lib.ptr(X), _lib.ptr(out), _lib.ptr(self.work),
+                                              self.nbytes, _lib.stream_ptr(self.dev)))
+        return out
+
+
+class PwdHost:
+    """Host-buffer plane-wave decomposition through the C ABI (``sfa_pwd_host_*``):
+    NumPy arrays in, NumPy array out; the H2D copy of X, the kernels and the D2H copy of the beams
+    are pipelined over frequency chunks inside the library."""
+
+    def __init__(self, Y_look, dn, Y_mic, T, precision="c64", form="auto", device=0, chunk_bins=0):
+        self.lib = _lib.require_cuda()
+        self.np_dtype = np.complex64 if precision == "c64" else np.complex128
+        Y_look = np.ascontiguousarray(Y_look, dtype=np.complex128)
+        Y_mic = np.ascontiguousarray(Y_mic, dtype=np.complex128)
+        dn = np.ascontiguousarray(dn, dtype=np.complex128)
+        if dn.ndim == 1:
+            dn = dn[None, :]
+        F, Q = dn.shape[0], Y_mic.shape[0]
+
+        class _S:                                   # duck-typed for _shape_of
+            pass
+        self.shape = _shape_of(torch.empty(Y_look.shape, device="meta"), torch.empty(dn.shape, device="meta"),
+                               torch.empty(Y_mic.shape, device="meta"), F, Q, int(T), precision, form)
+        self.ctx = ctypes.c_void_p()
+        _lib.check(self.lib.sfa_pwd_host_create(ctypes.byref(self.ctx), ctypes.byref(self.shape), int(device),
+                                                int(chunk_bins)))
+        _lib.check(self.lib.sfa_pwd_host_set_operators(self.ctx, Y_look.ctypes.data, Y_mic.ctypes.data,
+                                                       dn.ctypes.data))
+        self.in_shape = (F, Q, int(T))
+        self.out_shape = (F, Y_look.shape[0], int(T))
+        self._pinned = []
+
+    def pinned_empty(self, shape):
+        """Page-locked NumPy array (cudaHostAlloc) for X / out: makes the copies asynchronous."""
+        n = int(np.prod(shape)) * np.dtype(self.np_dtype).itemsize
+        p = ctypes.c_void_p()
+        _lib.check(self.lib.sfa_host_alloc(ctypes.byref(p), max(n, 1)))
+        self._pinned.append(p)
+        buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=self.np_dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __call__(self, X, out=None):
+        X = np.ascontiguousarray(X, dtype=self.np_dtype)
+        if X.ndim == 2:
+            X = X[:, :, None]
+        if X.shape != self.in_shape:
+            raise ValueError("X must have shape {}".format(self.in_shape))
+        if out is None:
+            out = np.empty(self.out_shape, dtype=self.np_dtype)
+        elif out.shape != self.out_shape or out.dtype != self.np_dtype or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous {} array of shape {}".format(self.np_dtype, self.out_shape))
+        _lib.check(self.lib.sfa_pwd_host_run(self.ctx, X.ctypes.data, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self.ctx:
+            self.lib.sfa_pwd_host_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p()
+        for p in self._pinned:
+            self.lib.sfa_host_free(p)
+        self._pinned = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

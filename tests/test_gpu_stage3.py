@@ -1,0 +1,221 @@
+"""GPU parity of stage 3 (plane-wave decomposition / steering) through the C ABI.
+Tolerance (north_star): FP32-class beam outputs <= 1e-5, measured normwise per frequency bin
+(max|q - q_ref| / max|q_ref| over the bin) because look directions in a null make an
+elementwise relative error meaningless; the FP64 path is held to 1e-11."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import sfa_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL64 = 1e-5
+TOL128 = 1e-11
+
+
+@pytest.fixture(scope="module")
+def mic():
+    import sfa_numpy_b200 as micarray
+    return micarray
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+def bin_err(q, ref):
+    q = q.reshape(q.shape[0], -1)
+    ref = ref.reshape(ref.shape[0], -1)
+    scale = np.max(np.abs(ref), axis=1)
+    scale = np.where(scale > 0, scale, 1.0)
+    return float(np.max(np.max(np.abs(q - ref), axis=1) / scale))
+
+
+def test_cgemm3x_direct(mic):
+    """out[b,n,m] = sum_k P[b,n,k] R[b,k,m] on tcgen05, ragged sizes, split-K, shared P, row scale."""
+    import torch
+    from sfa_numpy_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    cases = [(1, 64, 128, 8), (2, 70, 200, 64), (3, 5, 33, 3), (1, 130, 129, 100), (2, 64, 256, 37),
+             (1, 200, 1000, 64), (4, 17, 938, 9)]
+    for (B, Nn, Mm, K) in cases:
+        for shared in (False, True):
+            Pn = (rng.standard_normal((1 if shared else B, Nn, K)) + 1j * rng.standard_normal((1 if shared else B, Nn, K))).astype(np.complex64)
+            Rn = (rng.standard_normal((B, K, Mm)) + 1j * rng.standard_normal((B, K, Mm))).astype(np.complex64)
+            sc = (rng.standard_normal((B, Nn)) + 1j * rng.standard_normal((B, Nn))).astype(np.complex64)
+            P = torch.from_numpy(Pn).cuda()
+            R = torch.from_numpy(Rn).cuda()
+            S = torch.from_numpy(sc).cuda()
+            out = torch.full((B, Nn, Mm), float("nan"), dtype=torch.complex64, device="cuda")
+            for use_scale in (False, True):
+                _lib.check(lib.sfa_cgemm3x(B, Nn, Mm, K, _lib.ptr(P), K, 0 if shared else Nn * K, _lib.ptr(R), Mm,
+                                           K * Mm, _lib.ptr(out), Mm, Nn * Mm, _lib.ptr(S) if use_scale else None,
+                                           Nn, _lib.stream_ptr()))
+                ref = np.matmul(Pn.astype(np.complex128), Rn.astype(np.complex128))
+                if use_scale:
+                    ref = ref * sc[:, :, None].astype(np.complex128)
+                got = cpu(out)
+                assert np.isfinite(got.view(np.float32)).all(), (B, Nn, Mm, K, shared)
+                err = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
+                assert err < 2e-6, "cgemm3x %s shared=%s scale=%s err %.3e" % ((B, Nn, Mm, K), shared, use_scale, err)
+
+
+@pytest.mark.parametrize("precision,tol", [("c128", TOL128), ("c64", TOL64)])
+@pytest.mark.parametrize("form", ["steering", "factored", "auto"])
+def test_pwd_golden(mic, golden, precision, tol, form):
+    g = golden["pwd"]
+    A, R, S = mic.modal.angular, mic.modal.radial, mic.modal.steering
+    N = 4
+    Y_p = A.sht_matrix(N, g["sph_azi"], g["sph_colat"], g["sph_w"])
+    Y_q = A.sht_matrix(N, g["sph_azi_l"], np.pi / 2)
+    bn = R.spherical_pw(N, g["sph_k"], 0.042, "rigid")
+    dn, _ = R.regularize(1 / bn, 100, "softclip")
+    q = S.pwd(Y_q, dn, Y_p, g["sph_X"], precision=precision, form=form)
+    assert tuple(q.shape) == g["sph_q"].shape
+    assert bin_err(cpu(q), g["sph_q"]) < tol
+    # the literal reference chain on the GPU tensors (dense diagonal stack) gives the same
+    if precision == "c128":
+        import torch
+        D = R.diagonal_mode_mat(dn)
+        Alit = torch.matmul(torch.matmul(Y_q, D), Y_p.conj().T)
+        assert bin_err(cpu(Alit), g["sph_A"]) < 1e-12
+    N = 6
+    Psi_p = A.cht_matrix(N, g["circ_pol"], g["circ_w"])
+    Psi_q = A.cht_matrix(N, g["circ_pol_l"])
+    Bn = R.circular_pw(N, g["sph_k"], 0.1, "open")
+    Dn, _ = R.regularize(1 / Bn, 3000, "softclip")
+    q = S.pwd(Psi_q, Dn, Psi_p, g["circ_X"], precision=precision, form=form)
+    assert bin_err(cpu(q), g["circ_q"]) < tol
+
+
+def _dot_sph(v, u):
+    return (np.cos(v[0]) * np.sin(v[1]) * np.cos(u[0]) * np.sin(u[1]) +
+            np.sin(v[0]) * np.sin(v[1]) * np.sin(u[0]) * np.sin(u[1]) + np.cos(v[1]) * np.cos(u[1]))
+
+
+@pytest.mark.parametrize("precision,tol", [("c128", 1e-10), ("c64", TOL64)])
+def test_examples_end_to_end(mic, golden, precision, tol):
+    """The four reference example scripts, re-run through the GPU API, against the q the
+    unmodified scripts produced (fixtures) incl. the SURVEY 4.4 fingerprints."""
+    g = golden["examples"]
+    A, R, S = mic.modal.angular, mic.modal.radial, mic.modal.steering
+    k = g["open_spherical_k"]
+    azi, colat, w = A.grid_gauss(20)
+    azi_l = np.linspace(0, 2 * np.pi, 91, endpoint=False)
+    Y_p = A.sht_matrix(20, azi, colat, w)
+    Y_q = A.sht_matrix(20, azi_l, np.pi / 2)
+    p = np.exp(1j * k[:, None] * 1 * _dot_sph((azi, colat), (np.pi, np.pi / 2)))
+    for name, pp in (("open", p), ("rigid", g["rigid_spherical_p"])):
+        dn, _ = R.regularize(1 / R.spherical_pw(20, k, 1, name), 100, "softclip")
+        q = cpu(S.pwd(Y_q, dn, Y_p, pp, precision=precision))[:, :, 0]
+        ref = g[name + "_spherical_q"]
+        assert bin_err(q, ref) < tol, name
+        assert int(np.argmax(np.abs(q[50]))) == 45
+    pol, wc = A.grid_equal_polar_angle(30)
+    pol_l = np.linspace(0, 2 * np.pi, 180, endpoint=False)
+    Psi_p = A.cht_matrix(30, pol, wc)
+    Psi_q = A.cht_matrix(30, pol_l)
+    for name, a0, peak in (("open", 3000, 111), ("rigid", 100, 90)):
+        Dn, _ = R.regularize(1 / R.circular_pw(30, k, 1, name), a0, "softclip")
+        q = cpu(S.pwd(Psi_q, Dn, Psi_p, g[name + "_circular_p"], precision=precision))[:, :, 0]
+        assert bin_err(q, g[name + "_circular_q"]) < tol, name
+        assert int(np.argmax(np.abs(q[50]))) == peak
+
+
+SHAPES = [  # N, Q, L, F, T   (spherical unless N < 0 -> circular of order -N)
+    (4, 50, 360, 16, 256),      # cfg 1 shape, fewer bins
+    (4, 100, 360, 8, 1),        # Q > 64 -> split-K, T = 1
+    (8, 64, 2562, 6, 130),      # cfg 3 shape, fewer bins / frames (ragged m tile)
+    (8, 64, 65, 3, 938),        # ragged n tile, full T
+    (-16, 32, 360, 32, 7),      # cfg 2 (circular), odd T
+    (16, 289, 100, 4, 64),      # cfg 4: K = 289 (5 chunks)
+    (3, 5, 7, 2, 3),            # tiny everything
+    (2, 64, 128, 300, 128),     # many bins: several chunks
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("precision,tol", [("c128", TOL128), ("c64", TOL64)])
+def test_pwd_shapes(mic, shape, precision, tol):
+    N, Q, L, F, T = shape
+    A, R, S = mic.modal.angular, mic.modal.radial, mic.modal.steering
+    rng = np.random.default_rng(abs(N) * 1000 + Q)
+    k = O.wavenumbers(F) + 0.37
+    if N >= 0:
+        az, co, w = O.fibonacci_grid(Q)
+        azl, col, _ = O.fibonacci_grid(L)
+        Yp_ref, Yq_ref = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
+        Y_p, Y_q = A.sht_matrix(N, az, co, w), A.sht_matrix(N, azl, col)
+        dn_ref, _ = O.regularize(1 / O.spherical_pw(N, k, 0.042, "rigid"), 100, "Tikh")
+        dcols = O.repeat_n_m(dn_ref)
+        dn, _ = R.regularize(1 / R.spherical_pw(N, k, 0.042, "rigid"), 100, "Tikh")
+    else:
+        N = -N
+        pol = np.linspace(0, 2 * np.pi, Q, endpoint=False)
+        poll = np.linspace(0, 2 * np.pi, L, endpoint=False)
+        w = np.full(Q, 1 / Q)
+        Yp_ref, Yq_ref = O.cht_matrix(N, pol, w), O.cht_matrix(N, poll)
+        Y_p, Y_q = A.cht_matrix(N, pol, w), A.cht_matrix(N, poll)
+        dn_ref, _ = O.regularize(1 / O.circular_pw(N, k, 0.1, "open"), 3000, "softclip")
+        dcols = dn_ref
+        dn, _ = R.regularize(1 / R.circular_pw(N, k, 0.1, "open"), 3000, "softclip")
+    cd = np.complex64 if precision == "c64" else np.complex128
+    X = (rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(cd)
+    ref = O.pwd_factored(Yq_ref, dcols.reshape(F, -1), Yp_ref, X.astype(np.complex128))
+    for form in ("steering", "factored"):
+        q = cpu(S.pwd(Y_q, dn, Y_p, X, precision=precision, form=form))
+        assert q.shape == (F, L, T)
+        assert bin_err(q, ref) < tol, (form, bin_err(q, ref))
+
+
+def test_pwd_linearity_and_plan(mic):
+    """Size-independent property at the headline shape (fewer bins): linear in X, and the
+    reusable plan gives bit-identical results to the one-shot call."""
+    import torch
+    A, R, S = mic.modal.angular, mic.modal.radial, mic.modal.steering
+    N, Q, L, F, T = 8, 64, 2562, 40, 938
+    az, co, w = O.grid_equal_angle(3)
+    azl, col, _ = O.fibonacci_grid(L)
+    Y_p, Y_q = A.sht_matrix(N, az, co, w), A.sht_matrix(N, azl, col)
+    k = O.wavenumbers(1024)[:F] + 1.0
+    _, dn, _ = R.radial_filters(N, k, 0.042, "rigid", 100.0, "Tikh")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    X1 = torch.randn((F, Q, T), dtype=torch.complex64, device="cuda", generator=g)
+    X2 = torch.randn((F, Q, T), dtype=torch.complex64, device="cuda", generator=g)
+    plan = S.PwdPlan(Y_q, dn, Y_p, T)
+    q1, q2, q12 = plan(X1), plan(X2), plan(X1 + 2 * X2)
+    scale = float(q12.abs().max())
+    assert float((q12 - (q1 + 2 * q2)).abs().max()) / scale < 2e-6
+    assert torch.equal(q1, S.pwd(Y_q, dn, Y_p, X1))
+    # spot check 3 bins against the oracle
+    Yp_ref, Yq_ref = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
+    dn_ref, _ = O.regularize(1 / O.spherical_pw(N, k, 0.042, "rigid"), 100, "Tikh")
+    sel = [0, 17, F - 1]
+    ref = O.pwd_factored(Yq_ref, O.repeat_n_m(dn_ref)[sel], Yp_ref, cpu(X1)[sel].astype(np.complex128))
+    assert bin_err(cpu(q1)[sel], ref) < TOL64
+
+
+def test_pwd_host_path(mic):
+    """NumPy in / NumPy out through sfa_pwd_host_* (chunked H2D / compute / D2H pipeline)."""
+    S = mic.modal.steering
+    N, Q, L, F, T = 4, 50, 200, 37, 70
+    az, co, w = O.grid_gauss(N)
+    azl, col, _ = O.fibonacci_grid(L)
+    Yp_ref, Yq_ref = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
+    k = O.wavenumbers(F) + 0.5
+    dn_ref, _ = O.regularize(1 / O.spherical_pw(N, k, 0.042, "rigid"), 100, "softclip")
+    rng = np.random.default_rng(5)
+    for precision, tol in (("c64", TOL64), ("c128", TOL128)):
+        cd = np.complex64 if precision == "c64" else np.complex128
+        X = (rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(cd)
+        ref = O.pwd_factored(Yq_ref, O.repeat_n_m(dn_ref), Yp_ref, X.astype(np.complex128))
+        host = S.PwdHost(Yq_ref, dn_ref, Yp_ref, T, precision=precision, chunk_bins=8)
+        Xp = host.pinned_empty(X.shape)
+        Xp[...] = X
+        q = host(Xp)
+        assert bin_err(q, ref) < tol
+        q2 = host(X)                     # pageable memory works too
+        assert np.array_equal(q, q2)
+        host.close()
