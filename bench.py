@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the sfa-numpy modal beamforming hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[2], the config the headline metric is quoted on): rigid sphere,
+order N=8, 64 microphones (grid_equal_angle(3)), 1024 frequency bins, 2562 look directions,
+938 STFT frames (10 s at 48 kHz, NFFT 2048, hop 512), Tikhonov-regularised plane-wave
+decomposition.  One "step" = the whole hot path over that batch: SH matrices at the mics and
+look directions (stage 1), radial filters + fused regularised inverse (stage 2), and the per-bin
+steering contraction (stage 3) producing F*L*T beam outputs.
+
+Prints ONE JSON line (rank 0).  `value` = beam outputs/s with inputs resident in HBM (CUDA
+events, max over ranks); `e2e` = the same metric through the host-buffer C ABI call
+(sfa_pwd_host_run: pinned NumPy in, NumPy out, H2D + D2H inside the timed region).
+With N > 1 every rank processes its own batch of F bins (frequency sharding, no data-path
+collective): weak scaling.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(name="cfg3: rigid sphere N=8, 64 mics (grid_equal_angle(3)), F=1024 bins, L=2562 look dirs, "
+                "T=938 frames, Tikhonov a0=100",
+           N=8, F=1024, L=2562, T=938, r=0.042, a0=100.0, method="Tikh", setup="rigid")
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """Polls nvidia-smi during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                power.append(float(r[3]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] if power else sm
+        return {"sm_mhz": statistics.median(busy) if busy else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(O, cfg, rank):
+    azi, colat, w = O.grid_equal_angle(3)                 # 64 microphones
+    azl, col, _ = O.fibonacci_grid(cfg["L"])
+    k = O.wavenumbers(cfg["F"])
+    X = O.synth_spectra(cfg["F"], len(azi), cfg["T"], seed=rank)
+    return azi, colat, w, azl, col, k, X
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference path (the reference is Python/NumPy/SciPy and
+    cannot travel to the GPU box; oracle/ is its bit-exact restatement) on all host cores, on a
+    bounded sample of the same workload."""
+    from oracle import sfa_oracle as O
+    cfg = CFG
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    azi, colat, w, azl, col, k, _ = make_inputs(O, dict(cfg, F=1, T=1), 0)
+    k = O.wavenumbers(cfg["F"])
+    fs = 16                                               # bins per step (sample)
+    X = O.synth_spectra(fs, len(azi), cfg["T"], seed=0).astype(np.complex128)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        Y_p = O.sht_matrix(cfg["N"], azi, colat, w)
+        Y_q = O.sht_matrix(cfg["N"], azl, col)
+        bn = O.spherical_pw(cfg["N"], k, cfg["r"], cfg["setup"])
+        dn, _ = O.regularize(1 / bn, cfg["a0"], cfg["method"])
+        q = O.pwd_factored(Y_q, O.repeat_n_m(dn[:fs]), Y_p, X)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    outputs = fs * cfg["L"] * cfg["T"]
+    t = sum(times)
+    val = outputs * len(times) / t
+    sample = ("%d of %d bins per step (full L, T), complex128 NumPy/OpenBLAS factored form "
+              "+ SciPy stage 1/2 for all 1024 bins" % (fs, cfg["F"]))
+    line = {"impl": "reference", "metric": "beam outputs/sec", "value": val, "unit": "outputs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+            "config": {"workload": cfg["name"], "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "outputs/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": "outputs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline(O, cfg, azi, colat, w, azl, col, k):
+    """Oracle port on the host cores, bounded sample (~10-20 s)."""
+    fs = 16
+    X = O.synth_spectra(fs, len(azi), cfg["T"], seed=0).astype(np.complex128)
+    t_stage12 = time.perf_counter()
+    Y_p = O.sht_matrix(cfg["N"], azi, colat, w)
+    Y_q = O.sht_matrix(cfg["N"], azl, col)
+    bn = O.spherical_pw(cfg["N"], k, cfg["r"], cfg["setup"])
+    dn, _ = O.regularize(1 / bn, cfg["a0"], cfg["method"])
+    t_stage12 = time.perf_counter() - t_stage12
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        O.pwd_factored(Y_q, O.repeat_n_m(dn[:fs]), Y_p, X)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    outputs = fs * cfg["L"] * cfg["T"]
+    # whole-path equivalent: stage 1/2 once per step of F bins + stage 3 scaled to F bins
+    t_full = t_stage12 + best * cfg["F"] / fs
+    return {"value": cfg["F"] * cfg["L"] * cfg["T"] / t_full, "unit": "outputs/s", "cores": os.cpu_count(),
+            "kind": "port",
+            "sample": "stage 3 on %d of %d bins (full L, T; complex128 NumPy/OpenBLAS factored form, best of 3, "
+                      "%.3f s) scaled to %d bins + stage 1/2 once (%.3f s, SciPy, single thread)"
+                      % (fs, cfg["F"], best, cfg["F"], t_stage12),
+            "stage3_outputs_per_s": outputs / best, "stage12_s": t_stage12}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from oracle import sfa_oracle as O            # synthetic-input generator + cpu_baseline only
+    import __graft_entry__ as G
+    G.build()
+    import sfa_numpy_b200 as micarray
+    from sfa_numpy_b200 import _lib
+    import ctypes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    cfg = CFG
+    A, R, S = micarray.modal.angular, micarray.modal.radial, micarray.modal.steering
+
+    azi, colat, w, azl, col, k, Xh = make_inputs(O, cfg, rank)
+    Q = len(azi)
+    F, L, T, N = cfg["F"], cfg["L"], cfg["T"], cfg["N"]
+    d_azi, d_col, d_w = (torch.from_numpy(a).to(dev) for a in (azi, colat, w))
+    d_azl, d_coll = torch.from_numpy(azl).to(dev), torch.from_numpy(col).to(dev)
+    d_k = torch.from_numpy(k).to(dev)
+    X = torch.from_numpy(Xh).to(dev)
+    out = torch.empty((F, L, T), dtype=torch.complex64, device=dev)
+    plan = {}
+
+    def step():
+        Y_p = A.sht_matrix(N, d_azi, d_col, d_w)
+        Y_q = A.sht_matrix(N, d_azl, d_coll)
+        _, dn, _ = R.radial_filters(N, d_k, cfg["r"], cfg["setup"], cfg["a0"], cfg["method"])
+        if "p" not in plan:
+            plan["p"] = S.PwdPlan(Y_q, dn, Y_p, T)
+        p = plan["p"]
+        p.Y_look, p.Y_mic, p.dn = Y_q, Y_p, dn
+        return p(X, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.sfa_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.sfa_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * F * L * T * args.steps / (ms * 1e-3)
+
+    # ---- dominant kernel: average launch duration with CUDA events on its launching stream ----
+    lib.sfa_prof_enable(1)
+    for _ in range(max(2, min(args.steps, 5))):
+        step()
+    torch.cuda.synchronize()
+    tot, cnt = ctypes.c_double(), ctypes.c_longlong()
+    lib.sfa_prof_read(ctypes.byref(tot), ctypes.byref(cnt))
+    lib.sfa_prof_enable(0)
+    gemm_ms_per_step = tot.value / max(2, min(args.steps, 5))
+    # algorithmic bytes of the steering GEMM per step (complex64 I/O): X read + beams written +
+    # the steering matrices A_f it consumes  (DESIGN.md "roofline" section)
+    alg_bytes = 8.0 * F * T * (Q + L) + 8.0 * F * L * Q
+    alg_flops = 8.0 * F * L * Q * T
+    peaks, peak_src = load_peaks()
+    achieved = alg_bytes / (gemm_ms_per_step * 1e-3) / 1e9
+    roofline = {"kernel": "cgemm3x_kernel (tcgen05 3xTF32 steering GEMM)", "bound": "hbm",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
+                "launches_per_step": cnt.value / max(2, min(args.steps, 5)),
+                "kernel_ms_per_step": gemm_ms_per_step, "kernel_share_of_step": gemm_ms_per_step / (ms / args.steps),
+                "alg_bytes_per_step": alg_bytes, "alg_tflops_achieved": alg_flops / (gemm_ms_per_step * 1e-3) / 1e12}
+
+    line = {"metric": "beam outputs/sec", "value": value, "unit": "outputs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64 (3xTF32, FP32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": cfg["name"], "bins_per_gpu": F, "outputs_per_step_per_gpu": F * L * T,
+                       "l2": "inputs+outputs (20 GB) far larger than L2; no flush needed",
+                       "parallelism": "frequency-sharded x%d, no collective" % world},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+
+    # ---- e2e through the host-buffer C ABI ----
+    if rank == 0 and not args.no_e2e:
+        try:
+            torch.cuda.synchronize()
+            Yq_h = A.sht_matrix(N, d_azl, d_coll).cpu().numpy()
+            Yp_h = A.sht_matrix(N, d_azi, d_col, d_w).cpu().numpy()
+            dn_h = R.radial_filters(N, d_k, cfg["r"], cfg["setup"], cfg["a0"], cfg["method"])[1].cpu().numpy()
+            del out
+            torch.cuda.empty_cache()
+            host = S.PwdHost(Yq_h, dn_h, Yp_h, T, device=local, chunk_bins=0)
+            Xp = host.pinned_empty((F, Q, T))
+            Xp[...] = Xh
+            outp = host.pinned_empty((F, L, T))
+            host(Xp, out=outp)                          # warm-up
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                host(Xp, out=outp)
+            dt = (time.perf_counter() - t0) / args.e2e_steps
+            line["e2e"] = {"value": F * L * T / dt, "unit": "outputs/s", "h2d_bytes_per_step": int(Xp.nbytes),
+                           "d2h_bytes_per_step": int(outp.nbytes), "ms_per_step": dt * 1e3,
+                           "api": "sfa_pwd_host_run (C ABI, pinned host buffers, chunked H2D/compute/D2H pipeline)",
+                           "steps": args.e2e_steps}
+            host.close()
+        except Exception as e:                           # e.g. not enough pinned host memory
+            line["e2e"] = {"value": None, "unit": "outputs/s", "error": repr(e)}
+    if rank == 0 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(O, cfg, azi, colat, w, azl, col, k)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

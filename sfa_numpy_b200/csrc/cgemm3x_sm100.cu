@@ -346,6 +346,9 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
         }
     } else {
         // ===================== epilogue: TMEM -> regs -> global =====================
+        // lane = m: one store instruction of a warp writes 32 consecutive complex64 of row n
+        // (256 contiguous bytes).  The column loop is kept to a pointer bump + store per value;
+        // mode / row-scale / ragged-tile variants are hoisted out of it.
         const int quarter = warp & 3;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         int acc = 0;
@@ -355,6 +358,8 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
             const int mt = (int)(task - b * prm.m_tiles);
             const long long m = (long long)mt * kTileM + quarter * 32 + lane;
             const bool m_ok = m < prm.Mm;
+            float2* const out_bm = reinterpret_cast<float2*>(prm.out) + b * prm.strideO + (m_ok ? m : 0);
+            const float2* const scale_b = prm.rowscale ? prm.rowscale + b * prm.strideS : nullptr;
             for (int nt = 0; nt < prm.n_tiles; ++nt) {
                 mbar_wait(&bars->acc_full[acc], acc_phase);
                 tcgen05_fence_after();
@@ -372,28 +377,43 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
                     }
-                    if (m_ok) {
+                    const long long nbase = n0 + half * 32;
+                    long long left = prm.Nn - nbase;
+                    const int ncols = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+                    if (!m_ok || ncols == 0) continue;
+                    float2* o = out_bm + nbase * prm.ldo;
+                    if (scale_b) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const long long n = n0 + half * 32 + j;
-                            if (n < prm.Nn) {
-                                float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
-                                if (prm.rowscale) {
-                                    const float2 s = __ldg(prm.rowscale + b * prm.strideS + n);
-                                    const float tr = xr * s.x - xi * s.y;
-                                    xi = xr * s.y + xi * s.x;
-                                    xr = tr;
-                                }
-                                {
-                                    float2* o = reinterpret_cast<float2*>(prm.out) + b * prm.strideO + n * prm.ldo + m;
-                                    if (prm.out_mode == OUT_C64_ACCUM) {
-                                        const float2 old = *o;
-                                        xr += old.x;
-                                        xi += old.y;
-                                    }
-                                    *o = make_float2(xr, xi);
-                                }
+                            if (j < ncols) {
+                                const float2 sc = __ldg(scale_b + nbase + j);
+                                const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
+                                re[j] = __float_as_uint(xr * sc.x - xi * sc.y);
+                                im[j] = __float_as_uint(xr * sc.y + xi * sc.x);
                             }
+                        }
+                    }
+                    if (prm.out_mode == OUT_C64_ACCUM) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < ncols) {
+                                const float2 old = o[(long long)j * prm.ldo];
+                                re[j] = __float_as_uint(__uint_as_float(re[j]) + old.x);
+                                im[j] = __float_as_uint(__uint_as_float(im[j]) + old.y);
+                            }
+                        }
+                    }
+                    if (ncols == 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            *o = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+                            o += prm.ldo;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < ncols) *o = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+                            o += prm.ldo;
                         }
                     }
                 }

