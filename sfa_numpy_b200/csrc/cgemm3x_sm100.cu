@@ -124,6 +124,19 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of the (converged) warp; ptxas knows the region is single-lane, so warp-uniform
+// operands of UTCHMMA / UTMALDG go straight to uniform registers (no waterfall loops).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -227,7 +240,7 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
 
     if (warp == 0) {
         // ===================== TMA producer: stream P tiles =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&p_map) : "memory");
             int stage = 0;
             uint32_t phase = 0;
@@ -238,10 +251,14 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
                     mbar_wait(&bars->b_empty[stage], phase ^ 1);
                     unsigned char* dst = stage_base + (size_t)stage * kStageBytes;
                     mbar_arrive_expect_tx(&bars->b_full[stage], (uint32_t)(4 * kboxes * kBoxBytes));
-                    for (int pl = 0; pl < 4; ++pl)
-                        for (int kb = 0; kb < kboxes; ++kb)
-                            tma_load_3d(&p_map, &bars->b_full[stage], dst + (pl * 2 + kb) * kBoxBytes,
-                                        kb * kBoxK, nt * kTileN, pb * 4 + pl);
+#pragma unroll
+                    for (int pl = 0; pl < 4; ++pl) {
+                        tma_load_3d(&p_map, &bars->b_full[stage], dst + (pl * 2) * kBoxBytes, 0, nt * kTileN,
+                                    pb * 4 + pl);
+                        if (kboxes > 1)
+                            tma_load_3d(&p_map, &bars->b_full[stage], dst + (pl * 2 + 1) * kBoxBytes, kBoxK,
+                                        nt * kTileN, pb * 4 + pl);
+                    }
                     if (++stage == kStagesB) {
                         stage = 0;
                         phase ^= 1;
@@ -250,56 +267,60 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(kTileM, kTileN, false);
-            constexpr uint32_t idesc_neg = make_idesc(kTileM, kTileN, true);
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0, a_phase = 0;
-            for (long long task = blockIdx.x; task < prm.tasks; task += gridDim.x) {
-                mbar_wait(&bars->a_full, a_phase);
+        // ===================== MMA issuer (whole warp waits, one elected lane issues) =====================
+        constexpr uint32_t idesc = make_idesc(kTileM, kTileN, false);
+        constexpr uint32_t idesc_neg = make_idesc(kTileM, kTileN, true);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+        for (long long task = blockIdx.x; task < prm.tasks; task += gridDim.x) {
+            mbar_wait(&bars->a_full, a_phase);
+            for (int nt = 0; nt < prm.n_tiles; ++nt) {
+                mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+                mbar_wait(&bars->b_full[stage], phase);
                 tcgen05_fence_after();
-                for (int nt = 0; nt < prm.n_tiles; ++nt) {
-                    mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
-                    mbar_wait(&bars->b_full[stage], phase);
-                    tcgen05_fence_after();
+                if (elect_one_sync()) {
                     const uint32_t sbase = smem_u32(stage_base + (size_t)stage * kStageBytes);
+                    const uint64_t bdesc = make_b_desc(sbase);          // plane 0, k-box 0, k-step 0
                     const uint32_t d_re = tmem + acc * kAccCols;
                     const uint32_t d_im = d_re + kTileN;
-                    uint32_t first = 0;
-#pragma unroll 1
+                    const uint32_t a0 = tmem + kOperandCol0;
+#pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        // (A part, B part): (hi,hi) (hi,lo) (lo,hi)
-                        const int ap = (pass == 2) ? 2 : 0;       // plane offset of re within {re_hi,im_hi,re_lo,im_lo}
+                        // (A part, B part): (hi,hi) (hi,lo) (lo,hi); planes: re_hi, im_hi, re_lo, im_lo
+                        const int ap = (pass == 2) ? 2 : 0;
                         const int bp = (pass == 1) ? 2 : 0;
-                        const uint32_t a_re = tmem + kOperandCol0 + (ap + 0) * kMaxK;
-                        const uint32_t a_im = tmem + kOperandCol0 + (ap + 1) * kMaxK;
-#pragma unroll 1
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const int kb = ks >> 2, kk = ks & 3;
-                            const uint64_t b_re = make_b_desc(sbase + ((bp + 0) * 2 + kb) * kBoxBytes + kk * 32);
-                            const uint64_t b_im = make_b_desc(sbase + ((bp + 1) * 2 + kb) * kBoxBytes + kk * 32);
-                            umma_tf32_ts(d_re, a_re + ks * 8, b_re, idesc, first);
-                            umma_tf32_ts(d_im, a_re + ks * 8, b_im, idesc, first);
-                            first = 1;
-                            umma_tf32_ts(d_re, a_im + ks * 8, b_im, idesc_neg, 1);
-                            umma_tf32_ts(d_im, a_im + ks * 8, b_re, idesc, 1);
+#pragma unroll
+                        for (int ks = 0; ks < kMaxK / 8; ++ks) {
+                            if (ks < ksteps) {
+                                const int kb = ks >> 2, kk = ks & 3;
+                                // the start-address field counts 16-byte units; offsets stay inside it
+                                const uint64_t b_re = bdesc + (uint64_t)((((bp + 0) * 2 + kb) * kBoxBytes + kk * 32) >> 4);
+                                const uint64_t b_im = bdesc + (uint64_t)((((bp + 1) * 2 + kb) * kBoxBytes + kk * 32) >> 4);
+                                const uint32_t a_re = a0 + (ap + 0) * kMaxK + ks * 8;
+                                const uint32_t a_im = a0 + (ap + 1) * kMaxK + ks * 8;
+                                const uint32_t accum = (pass == 0 && ks == 0) ? 0u : 1u;
+                                umma_tf32_ts(d_re, a_re, b_re, idesc, accum);
+                                umma_tf32_ts(d_im, a_re, b_im, idesc, accum);
+                                umma_tf32_ts(d_re, a_im, b_im, idesc_neg, 1u);
+                                umma_tf32_ts(d_im, a_im, b_re, idesc, 1u);
+                            }
                         }
                     }
                     tcgen05_commit(&bars->b_empty[stage]);
                     tcgen05_commit(&bars->acc_full[acc]);
-                    if (++stage == kStagesB) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                    if (++acc == 2) {
-                        acc = 0;
-                        acc_phase ^= 1;
-                    }
+                    if (nt == prm.n_tiles - 1) tcgen05_commit(&bars->a_empty);
                 }
-                tcgen05_commit(&bars->a_empty);
-                a_phase ^= 1;
+                __syncwarp();
+                if (++stage == kStagesB) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
             }
+            a_phase ^= 1;
         }
     } else if (warp < 6) {
         // ===================== A-operand loaders: global -> regs -> TMEM =====================
