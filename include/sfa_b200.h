@@ -55,7 +55,9 @@ enum sfa_radial_kind {
 };
 enum sfa_precision {
     SFA_PREC_C64_3XTF32 = 0,  /* complex64 in/out, tcgen05 kind::tf32 with hi/lo split (3 passes), FP32 accumulate */
-    SFA_PREC_C128_FP64 = 1    /* complex128 in/out, FP64 FMA on the CUDA cores                                    */
+    SFA_PREC_C128_FP64 = 1,   /* complex128 in/out, FP64 FMA on the CUDA cores                                    */
+    SFA_PREC_C64_TF32_BF16 = 2 /* complex64 in/out, hi*hi as kind::tf32 + (hi*lo + lo*hi) as one bf16 pass: 2/3 of
+                                  the tensor work of 3xTF32, cross terms rounded to bf16 (~2^-19 relative)        */
 };
 
 const char* sfa_strerror(int status);
@@ -150,12 +152,13 @@ int sfa_pwd_apply(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* Y
 
 /* Batched complex GEMM building block used by sfa_pwd_apply, exposed for tests:
  *   out[b, n, m] = sum_k P[b?, n, k] * R[b, k, m]  (* rowscale[b, n] if given)
- * complex64, 3xTF32 on tcgen05.  ldP, ldR, ldo in elements; strideP = 0 shares P. */
+ * complex64 on tcgen05, 3xTF32 (hybrid = 0) or TF32+BF16 (hybrid = 1).  ldP, ldR, ldo in elements;
+ * strideP = 0 shares P across the batch. */
 int sfa_cgemm3x(int64_t B, int64_t Nn, int64_t Mm, int64_t K,
                 const sfa_c64* P, int64_t ldP, int64_t strideP,
                 const sfa_c64* R, int64_t ldR, int64_t strideR,
                 sfa_c64* out, int64_t ldo, int64_t strideO,
-                const sfa_c64* rowscale, int64_t strideS, void* stream);
+                const sfa_c64* rowscale, int64_t strideS, int hybrid, void* stream);
 
 /* Host-buffer plane-wave decomposition: the call a reference user makes with NumPy
  * arrays.  Creates device buffers/streams once; `run` copies X (pinned or pageable

@@ -44,7 +44,7 @@ SIGNATURES = {
     "sfa_pwd_apply": (c_int, [ctypes.POINTER(PwdShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_void_p]),
     "sfa_cgemm3x": (c_int, [c_int64] * 4 + [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
-                                            c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+                                            c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "sfa_pwd_host_create": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(PwdShape), c_int, c_int64]),
     "sfa_pwd_host_set_operators": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfa_pwd_host_run": (c_int, [c_void_p, c_void_p, c_void_p]),

@@ -8,6 +8,12 @@
 // product is 4 real products into two accumulators (Re, Im); the minus sign of
 // Re -= Ri*Pi uses the instruction descriptor's negate-A bit.
 //
+// Second mode ("hybrid", kHybrid): hi*hi runs as one kind::tf32 pass and the two cross terms
+// hi*lo + lo*hi run as ONE kind::f16 (bf16) pass over a K extent interleaved as
+// (hi_bf16(k), lo_bf16(k)) on the A side and (lo_bf16(k), hi_bf16(k)) on the B side, packed two
+// bf16 per 32-bit slot -- same addresses, same 8 slots per k-step, 2/3 of the tensor work.
+// The cross terms are ~2^-11 of the result, so their bf16 rounding (2^-9) costs ~2^-19 relative.
+//
 // This is stage 3 of the hot path: the plane-wave-decomposition/steering
 // contraction of the reference's example idiom
 //     A = matmul(matmul(Y_q, D), conj(Y_p.T)); q = matmul(A, p)
@@ -137,6 +143,23 @@ __device__ __forceinline__ bool elect_one_sync() {
         : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// two bf16 in one 32-bit slot: `first` is the lower-addressed (even-k) element
+__device__ __forceinline__ uint32_t pack_bf16(float first, float second) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));
+    return r;
+}
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -185,8 +208,9 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 }
 
 // Instruction descriptor: F32 accumulate, TF32 x TF32, K-major A and B.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)(N >> 3) << 17) |
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a, bool bf16 = false) {
+    const uint32_t fmt = bf16 ? 1u : 2u;        // F16F32Format: 1 = BF16, 2 = TF32
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
 
@@ -201,6 +225,7 @@ struct __align__(8) Barriers {
     uint32_t pad;
 };
 
+template <bool kHybrid>
 __global__ void __launch_bounds__(kThreads, 1)
 cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) {
     extern __shared__ unsigned char smem_dyn[];
@@ -268,8 +293,9 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp waits, one elected lane issues) =====================
-        constexpr uint32_t idesc = make_idesc(kTileM, kTileN, false);
-        constexpr uint32_t idesc_neg = make_idesc(kTileM, kTileN, true);
+        // the last n-tile may be narrow: issue it with UMMA N = remaining rows rounded up to 16
+        const int n_tail = (int)(prm.Nn - (long long)(prm.n_tiles - 1) * kTileN);
+        const int n_tail16 = ((n_tail + 15) >> 4) << 4;
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0, a_phase = 0;
         for (long long task = blockIdx.x; task < prm.tasks; task += gridDim.x) {
@@ -278,17 +304,25 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
                 mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
                 mbar_wait(&bars->b_full[stage], phase);
                 tcgen05_fence_after();
+                const int n_mma = (nt == prm.n_tiles - 1) ? n_tail16 : kTileN;
+                const uint32_t idesc = make_idesc(kTileM, n_mma, false);
+                const uint32_t idesc_neg = make_idesc(kTileM, n_mma, true);
+                const uint32_t idesc_bf = make_idesc(kTileM, n_mma, false, true);
+                const uint32_t idesc_bf_neg = make_idesc(kTileM, n_mma, true, true);
                 if (elect_one_sync()) {
                     const uint32_t sbase = smem_u32(stage_base + (size_t)stage * kStageBytes);
                     const uint64_t bdesc = make_b_desc(sbase);          // plane 0, k-box 0, k-step 0
                     const uint32_t d_re = tmem + acc * kAccCols;
                     const uint32_t d_im = d_re + kTileN;
                     const uint32_t a0 = tmem + kOperandCol0;
+                    constexpr int kPasses = kHybrid ? 2 : 3;
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        // (A part, B part): (hi,hi) (hi,lo) (lo,hi); planes: re_hi, im_hi, re_lo, im_lo
-                        const int ap = (pass == 2) ? 2 : 0;
-                        const int bp = (pass == 1) ? 2 : 0;
+                    for (int pass = 0; pass < kPasses; ++pass) {
+                        // planes: {re_hi, im_hi, re_x, im_x}; x = lo (fp32) or packed bf16 (hi, lo) pairs.
+                        // 3xTF32: (A,B) = (hi,hi) (hi,lo) (lo,hi).  hybrid: tf32 (hi,hi), then bf16 (x,x).
+                        const int ap = kHybrid ? (pass == 1 ? 2 : 0) : ((pass == 2) ? 2 : 0);
+                        const int bp = kHybrid ? (pass == 1 ? 2 : 0) : ((pass == 1) ? 2 : 0);
+                        const bool bf = kHybrid && pass == 1;
 #pragma unroll
                         for (int ks = 0; ks < kMaxK / 8; ++ks) {
                             if (ks < ksteps) {
@@ -299,10 +333,17 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
                                 const uint32_t a_re = a0 + (ap + 0) * kMaxK + ks * 8;
                                 const uint32_t a_im = a0 + (ap + 1) * kMaxK + ks * 8;
                                 const uint32_t accum = (pass == 0 && ks == 0) ? 0u : 1u;
-                                umma_tf32_ts(d_re, a_re, b_re, idesc, accum);
-                                umma_tf32_ts(d_im, a_re, b_im, idesc, accum);
-                                umma_tf32_ts(d_re, a_im, b_im, idesc_neg, 1u);
-                                umma_tf32_ts(d_im, a_im, b_re, idesc, 1u);
+                                if (bf) {
+                                    umma_bf16_ts(d_re, a_re, b_re, idesc_bf, accum);
+                                    umma_bf16_ts(d_im, a_re, b_im, idesc_bf, accum);
+                                    umma_bf16_ts(d_re, a_im, b_im, idesc_bf_neg, 1u);
+                                    umma_bf16_ts(d_im, a_im, b_re, idesc_bf, 1u);
+                                } else {
+                                    umma_tf32_ts(d_re, a_re, b_re, idesc, accum);
+                                    umma_tf32_ts(d_im, a_re, b_im, idesc, accum);
+                                    umma_tf32_ts(d_re, a_im, b_im, idesc_neg, 1u);
+                                    umma_tf32_ts(d_im, a_im, b_re, idesc, 1u);
+                                }
                             }
                         }
                     }
@@ -333,16 +374,21 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
             const long long m = (long long)mt * kTileM + quarter * 32 + lane;
             const bool m_ok = m < prm.Mm;
             const float2* src = prm.R + b * prm.strideR + (m_ok ? m : 0);
+            float2 v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                v[j] = (m_ok && j < prm.K) ? __ldg(src + (long long)j * prm.ldR) : make_float2(0.f, 0.f);
             // wait until the MMAs of the previous task no longer read the operand columns
             mbar_wait(&bars->a_empty, a_phase ^ 1);
             tcgen05_fence_after();
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
-                float2 v[32];
+                if (half == 1) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int k = half * 32 + j;
-                    v[j] = (m_ok && k < prm.K) ? __ldg(src + (long long)k * prm.ldR) : make_float2(0.f, 0.f);
+                    for (int j = 0; j < 32; ++j) {
+                        const int k = 32 + j;
+                        v[j] = (m_ok && k < prm.K) ? __ldg(src + (long long)k * prm.ldR) : make_float2(0.f, 0.f);
+                    }
                 }
                 uint32_t w[32];
                 const uint32_t col = tmem + lane_base + kOperandCol0 + half * 32;
@@ -350,13 +396,19 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
                 for (int j = 0; j < 32; ++j) w[j] = to_tf32(v[j].x);
                 SFA_TMEM_ST32(col + 0 * kMaxK, w);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j].x - __uint_as_float(to_tf32(v[j].x)));
+                for (int j = 0; j < 32; ++j) {
+                    const float h = __uint_as_float(to_tf32(v[j].x));
+                    w[j] = kHybrid ? pack_bf16(h, v[j].x - h) : __float_as_uint(v[j].x - h);   // A side: (hi, lo)
+                }
                 SFA_TMEM_ST32(col + 2 * kMaxK, w);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) w[j] = to_tf32(v[j].y);
                 SFA_TMEM_ST32(col + 1 * kMaxK, w);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j].y - __uint_as_float(to_tf32(v[j].y)));
+                for (int j = 0; j < 32; ++j) {
+                    const float h = __uint_as_float(to_tf32(v[j].y));
+                    w[j] = kHybrid ? pack_bf16(h, v[j].y - h) : __float_as_uint(v[j].y - h);
+                }
                 SFA_TMEM_ST32(col + 3 * kMaxK, w);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -474,7 +526,7 @@ static EncodeTiledFn get_encode_fn() {
 // P planar-split layout: [batches][4 planes][Nn][Kp] fp32, Kp % 4 == 0.
 int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* Pplanar, long long Kp,
                    int p_shared, const float2* R, long long ldR, long long strideR, float* out, long long ldo,
-                   long long strideO, int out_mode, const float2* rowscale, long long strideS,
+                   long long strideO, int out_mode, const float2* rowscale, long long strideS, int hybrid,
                    cudaStream_t st) {
     if (B <= 0 || Nn <= 0 || Mm <= 0) return SFA_OK;
     if (K <= 0 || K > kMaxK || (Kp & 3) || Kp < K) return SFA_ERR_INVALID;
@@ -515,12 +567,14 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     const size_t smem = (size_t)kStagesB * kStageBytes + sizeof(Barriers) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        SFA_CUDA_CHECK(cudaFuncSetAttribute(cgemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SFA_CUDA_CHECK(cudaFuncSetAttribute(cgemm3x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SFA_CUDA_CHECK(cudaFuncSetAttribute(cgemm3x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     long long grid = prm.tasks < sm_count() ? prm.tasks : sm_count();
     prof_begin(st);
-    cgemm3x_kernel<<<(unsigned)grid, kThreads, smem, st>>>(map, prm);
+    if (hybrid) cgemm3x_kernel<true><<<(unsigned)grid, kThreads, smem, st>>>(map, prm);
+    else cgemm3x_kernel<false><<<(unsigned)grid, kThreads, smem, st>>>(map, prm);
     prof_end(st);
     SFA_LAUNCH_CHECK();
     return SFA_OK;

@@ -21,7 +21,7 @@ namespace sfa {
 
 int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* Pplanar, long long Kp,
                    int p_shared, const float2* R, long long ldR, long long strideR, float* out, long long ldo,
-                   long long strideO, int out_mode, const float2* rowscale, long long strideS,
+                   long long strideO, int out_mode, const float2* rowscale, long long strideS, int hybrid,
                    cudaStream_t st);
 
 constexpr int kOutC64 = 0, kOutAccum = 2;
@@ -30,6 +30,13 @@ __device__ __forceinline__ uint32_t tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
+}
+// B-side slot of the hybrid mode: two bf16 in 32 bits, (lo, hi) = (even k, odd k) of the
+// interleaved bf16 K axis (the A side holds (hi, lo), see cgemm3x_sm100.cu)
+__device__ __forceinline__ float pack_bf16_lo_hi(float hi, float lo) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return __uint_as_float(r);
 }
 // x (double) -> hi = tf32(x), lo = float(x - hi)
 __device__ __forceinline__ void split_from_double(double x, float& hi, float& lo) {
@@ -46,7 +53,7 @@ __device__ __forceinline__ int order_of_column(int i) {     // radial.repeat_n_m
 
 // S [rows x cols] complex128 (ld) -> planar split P[4][Nn][Kp]; P(n,k) = S(n,k) or conj(S(k,n)).
 __global__ void split_planar_kernel(const double2* __restrict__ S, long long ld, int conj_transpose,
-                                    long long Nn, long long K, long long Kp, float* __restrict__ P) {
+                                    long long Nn, long long K, long long Kp, int hybrid, float* __restrict__ P) {
     const long long total = Nn * Kp;
     const long long plane = Nn * Kp;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -61,10 +68,10 @@ __global__ void split_planar_kernel(const double2* __restrict__ S, long long ld,
         float h, l;
         split_from_double(re, h, l);
         P[i] = h;
-        P[2 * plane + i] = l;
+        P[2 * plane + i] = hybrid ? pack_bf16_lo_hi(h, l) : l;
         split_from_double(im, h, l);
         P[plane + i] = h;
-        P[3 * plane + i] = l;
+        P[3 * plane + i] = hybrid ? pack_bf16_lo_hi(h, l) : l;
     }
 }
 
@@ -116,38 +123,62 @@ __global__ void group_products_kernel(const double2* __restrict__ YL, const doub
 
 // Steering matrices of a frequency chunk, written pre-split for the tensor-core GEMM:
 //   A[f][plane][l*Qp + q] = split( sum_g d[f][g] * G[g][l*Qp+q] )
+// One thread per (l, q) keeps its NG group products in registers and walks the bins of the
+// slab; every store instruction of a warp writes 128 contiguous bytes of one plane.
+// HBM-store-bound: 16 B out per steering entry.
+template <int NG>
 __global__ void __launch_bounds__(256)
 steer_build_split_kernel(const float2* __restrict__ G, const double2* __restrict__ d, int Cd, int ngroups,
-                         long long f0, int nf, long long LQ, float* __restrict__ A) {
-    extern __shared__ float2 sh_d[];                    // [nf][ngroups]
-    for (int i = threadIdx.x; i < nf * ngroups; i += blockDim.x) {
-        const int f = i / ngroups, g = i - f * ngroups;
-        const double2 v = d[(f0 + f) * Cd + g];
-        sh_d[i] = make_float2((float)v.x, (float)v.y);
+                         long long f0, int nf, long long LQ, int hybrid, float* __restrict__ A) {
+    extern __shared__ float2 sh_d[];                    // [nf][NG], zero padded
+    for (int i = threadIdx.x; i < nf * NG; i += blockDim.x) {
+        const int f = i / NG, g = i - f * NG;
+        float2 v = make_float2(0.f, 0.f);
+        if (g < ngroups) {
+            const double2 dv = d[(f0 + f) * Cd + g];
+            v = make_float2((float)dv.x, (float)dv.y);
+        }
+        sh_d[i] = v;
     }
     __syncthreads();
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < LQ;
          e += (long long)gridDim.x * blockDim.x) {
-        float2 g[64];
-#pragma unroll 1
-        for (int c = 0; c < ngroups; ++c) g[c] = __ldg(G + (long long)c * LQ + e);
+        float2 g[NG];
+#pragma unroll
+        for (int c = 0; c < NG; ++c) g[c] = (c < ngroups) ? __ldg(G + (long long)c * LQ + e) : make_float2(0.f, 0.f);
+        float* o = A + e;
+#pragma unroll 2
         for (int f = 0; f < nf; ++f) {
             float ar = 0.f, ai = 0.f;
-            for (int c = 0; c < ngroups; ++c) {
-                const float2 dv = sh_d[f * ngroups + c];
+#pragma unroll
+            for (int c = 0; c < NG; ++c) {
+                const float2 dv = sh_d[f * NG + c];
                 ar = fmaf(dv.x, g[c].x, ar);
                 ar = fmaf(-dv.y, g[c].y, ar);
                 ai = fmaf(dv.x, g[c].y, ai);
                 ai = fmaf(dv.y, g[c].x, ai);
             }
-            float* o = A + (long long)f * 4 * LQ + e;
             const float hr = __uint_as_float(tf32_rna(ar)), hi = __uint_as_float(tf32_rna(ai));
-            o[0] = hr;
-            o[LQ] = hi;
-            o[2 * LQ] = ar - hr;
-            o[3 * LQ] = ai - hi;
+            __stcs(o, hr);
+            __stcs(o + LQ, hi);
+            __stcs(o + 2 * LQ, hybrid ? pack_bf16_lo_hi(hr, ar - hr) : ar - hr);
+            __stcs(o + 3 * LQ, hybrid ? pack_bf16_lo_hi(hi, ai - hi) : ai - hi);
+            o += 4 * LQ;
         }
     }
+}
+
+static int launch_steer_build(const float2* G, const double2* d, int Cd, long long f0, int nf, long long LQ,
+                              int hybrid, float* A, cudaStream_t st) {
+    const unsigned grid = (unsigned)ceil_div(LQ, 256);
+    if (Cd <= 16)
+        steer_build_split_kernel<16><<<grid, 256, (size_t)nf * 16 * sizeof(float2), st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
+    else if (Cd <= 32)
+        steer_build_split_kernel<32><<<grid, 256, (size_t)nf * 32 * sizeof(float2), st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
+    else
+        steer_build_split_kernel<64><<<grid, 256, (size_t)nf * 64 * sizeof(float2), st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
 }
 
 // FP64 variant: A[f][l*Q + q] complex128
@@ -276,8 +307,13 @@ struct Plan {
     long long Qp, Mp, Tld;      // padded k extents / leading dims
     int ngroups;
     long long fc;               // bins per chunk
-    size_t off_G, off_A, off_P1, off_P2, off_dcols, off_Z, total;
+    size_t off_G, off_A, off_P1, off_P2, off_dcols, off_Z, total, a_slab;
 };
+
+static inline bool is_c64(const sfa_pwd_shape* s) {
+    return s->precision == SFA_PREC_C64_3XTF32 || s->precision == SFA_PREC_C64_TF32_BF16;
+}
+static inline int is_hybrid(const sfa_pwd_shape* s) { return s->precision == SFA_PREC_C64_TF32_BF16 ? 1 : 0; }
 
 static double gemm_cost(double Nn, double Mm, double K, double batches) {
     // MMA work in padded tile units plus the split-K read-modify-write traffic, in seconds (rough).
@@ -289,12 +325,12 @@ static double gemm_cost(double Nn, double Mm, double K, double batches) {
 
 static int make_plan(const sfa_pwd_shape* s, Plan* p) {
     if (!s || s->F < 0 || s->L <= 0 || s->Q <= 0 || s->T <= 0 || s->M <= 0 || s->Cd <= 0) return SFA_ERR_INVALID;
-    if (s->precision != SFA_PREC_C64_3XTF32 && s->precision != SFA_PREC_C128_FP64) return SFA_ERR_INVALID;
+    if (!is_c64(s) && s->precision != SFA_PREC_C128_FP64) return SFA_ERR_INVALID;
     if (s->d_is_per_order) {
         const int N1 = s->Cd;
         if (N1 * N1 != s->M) return SFA_ERR_INVALID;
     } else if (s->Cd != s->M) return SFA_ERR_INVALID;
-    const bool c64 = s->precision == SFA_PREC_C64_3XTF32;
+    const bool c64 = is_c64(s);
     p->Qp = round_up(s->Q, 4);
     p->Mp = round_up(s->M, 4);
     p->Tld = s->T;
@@ -311,7 +347,7 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
     p->form = form;
     // bins per chunk: keep the per-chunk scratch around `budget` bytes and the task count a
     // multiple of the SM count (tasks = bins * ceil(T/128)) so persistent CTAs finish together.
-    double budget = 96.0 * 1024 * 1024;
+    double budget = 256.0 * 1024 * 1024;   // per slab
     if (const char* e = getenv("SFA_PWD_CHUNK_MB")) budget = atof(e) * 1024 * 1024;
     const double per_bin = (form == 1) ? (double)s->L * p->Qp * 16.0 : (double)s->M * p->Tld * (c64 ? 8.0 : 16.0);
     const long long m_tiles = ceil_div(s->T, 128);
@@ -322,13 +358,14 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
     if (fc > s->F) fc = s->F > 0 ? s->F : 1;
     p->fc = fc;
     size_t off = 0;
-    p->off_G = p->off_A = p->off_P1 = p->off_P2 = p->off_dcols = p->off_Z = 0;
+    p->off_G = p->off_A = p->off_P1 = p->off_P2 = p->off_dcols = p->off_Z = p->a_slab = 0;
     const size_t esz = c64 ? 8 : 16;
     if (form == 1) {
         p->off_G = off;
         off += align_up((size_t)s->Cd * s->L * p->Qp * esz);
-        p->off_A = off;
-        off += align_up((size_t)fc * s->L * p->Qp * 16);      // 4 fp32 planes == one complex128
+        p->off_A = off;                                       // two slabs: build(i+1) overlaps gemm(i)
+        p->a_slab = align_up((size_t)fc * s->L * p->Qp * 16); // 4 fp32 planes == one complex128
+        off += 2 * p->a_slab;
     } else {
         p->off_P1 = off;
         off += align_up((size_t)s->M * p->Qp * 16);
@@ -345,12 +382,12 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
 
 static int cgemm_splitk(long long B, long long Nn, long long Mm, long long K, const float* Pp, long long Kp,
                         int p_shared, const float2* R, long long ldR, long long strideR, float2* out, long long ldo,
-                        long long strideO, const float2* rowscale, long long strideS, cudaStream_t st) {
+                        long long strideO, const float2* rowscale, long long strideS, int hybrid, cudaStream_t st) {
     for (long long k0 = 0; k0 < K; k0 += 64) {
         const int kc = (int)((K - k0 < 64) ? (K - k0) : 64);
         int rc = launch_cgemm3x(B, Nn, Mm, kc, Pp + k0, Kp, p_shared, R + k0 * ldR, ldR, strideR,
                                 reinterpret_cast<float*>(out), ldo, strideO, k0 == 0 ? kOutC64 : kOutAccum,
-                                rowscale, strideS, st);
+                                rowscale, strideS, hybrid, st);
         if (rc != SFA_OK) return rc;
     }
     return SFA_OK;
@@ -361,7 +398,7 @@ static int pwd_prepare(const sfa_pwd_shape* s, const Plan& p, const double2* yl,
                        unsigned char* w, cudaStream_t st) {
     const long long L = s->L, Q = s->Q;
     const int M = s->M, Cd = s->Cd;
-    const bool c64 = s->precision == SFA_PREC_C64_3XTF32;
+    const bool c64 = is_c64(s);
     const long long LQ = L * p.Qp;
     if (p.form == 1) {
         if (c64)
@@ -372,10 +409,10 @@ static int pwd_prepare(const sfa_pwd_shape* s, const Plan& p, const double2* yl,
                                                                       reinterpret_cast<double2*>(w + p.off_G));
         SFA_LAUNCH_CHECK();
     } else if (c64) {
-        split_planar_kernel<<<grid1d((long long)M * p.Qp), 256, 0, st>>>(yq, M, 1, M, Q, p.Qp,
+        split_planar_kernel<<<grid1d((long long)M * p.Qp), 256, 0, st>>>(yq, M, 1, M, Q, p.Qp, is_hybrid(s),
                                                                         reinterpret_cast<float*>(w + p.off_P1));
         SFA_LAUNCH_CHECK();
-        split_planar_kernel<<<grid1d(L * p.Mp), 256, 0, st>>>(yl, M, 0, L, M, p.Mp,
+        split_planar_kernel<<<grid1d(L * p.Mp), 256, 0, st>>>(yl, M, 0, L, M, p.Mp, is_hybrid(s),
                                                              reinterpret_cast<float*>(w + p.off_P2));
         SFA_LAUNCH_CHECK();
     } else {
@@ -392,7 +429,7 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
                         const void* X, void* out, unsigned char* w, cudaStream_t st) {
     const long long L = s->L, Q = s->Q, T = s->T;
     const int M = s->M, Cd = s->Cd;
-    const bool c64 = s->precision == SFA_PREC_C64_3XTF32;
+    const bool c64 = is_c64(s);
     const long long LQ = L * p.Qp;
     int rc;
     if (c64) {
@@ -403,11 +440,10 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
             float* A = reinterpret_cast<float*>(w + p.off_A);
             for (long long g0 = 0; g0 < nf; g0 += 64) {          // d staged through smem, <= 64 bins a time
                 const int ng = (int)((nf - g0 < 64) ? nf - g0 : 64);
-                steer_build_split_kernel<<<grid1d(LQ), 256, (size_t)ng * Cd * sizeof(float2), st>>>(
-                    G, dd, Cd, Cd, g0, ng, LQ, A + g0 * 4 * LQ);
-                SFA_LAUNCH_CHECK();
+                rc = launch_steer_build(G, dd, Cd, g0, ng, LQ, is_hybrid(s), A + g0 * 4 * LQ, st);
+                if (rc != SFA_OK) return rc;
             }
-            return cgemm_splitk(nf, L, T, Q, A, p.Qp, 0, x, T, Q * T, o, T, L * T, nullptr, 0, st);
+            return cgemm_splitk(nf, L, T, Q, A, p.Qp, 0, x, T, Q * T, o, T, L * T, nullptr, 0, is_hybrid(s), st);
         }
         const float* P1 = reinterpret_cast<const float*>(w + p.off_P1);
         const float* P2 = reinterpret_cast<const float*>(w + p.off_P2);
@@ -415,9 +451,9 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
         float2* Z = reinterpret_cast<float2*>(w + p.off_Z);
         expand_diag_kernel<float2><<<grid1d(nf * M), 256, 0, st>>>(dd, nf, Cd, M, s->d_is_per_order, dcols);
         SFA_LAUNCH_CHECK();
-        rc = cgemm_splitk(nf, M, T, Q, P1, p.Qp, 1, x, T, Q * T, Z, p.Tld, (long long)M * p.Tld, dcols, M, st);
+        rc = cgemm_splitk(nf, M, T, Q, P1, p.Qp, 1, x, T, Q * T, Z, p.Tld, (long long)M * p.Tld, dcols, M, is_hybrid(s), st);
         if (rc != SFA_OK) return rc;
-        return cgemm_splitk(nf, L, T, M, P2, p.Mp, 1, Z, p.Tld, (long long)M * p.Tld, o, T, L * T, nullptr, 0, st);
+        return cgemm_splitk(nf, L, T, M, P2, p.Mp, 1, Z, p.Tld, (long long)M * p.Tld, o, T, L * T, nullptr, 0, is_hybrid(s), st);
     }
     const double2* x = reinterpret_cast<const double2*>(X);
     double2* o = reinterpret_cast<double2*>(out);
@@ -445,7 +481,62 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
     return SFA_OK;
 }
 
-static inline size_t elem_bytes(const sfa_pwd_shape* s) { return s->precision == SFA_PREC_C64_3XTF32 ? 8 : 16; }
+// Form 1, several chunks: the (HBM-store-bound) steering-matrix build of chunk i+1 runs on a
+// side stream while the (tensor-bound) GEMM of chunk i runs on the caller's stream.  The GEMM
+// CTAs leave ~30 KB of shared memory and ~12 K registers per SM free, enough for the build CTAs
+// to be co-resident.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, built[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+};
+static SideStream* side_for_current_device() {
+    static SideStream side[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream& s = side[dev];
+    if (!s.stream) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+        for (int i = 0; i < 2; ++i) {
+            cudaEventCreateWithFlags(&s.built[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&s.done[i], cudaEventDisableTiming);
+        }
+    }
+    return &s;
+}
+
+static int pwd_steering_pipelined(const sfa_pwd_shape* s, const Plan& p, const double2* dd, const float2* x,
+                                  float2* o, unsigned char* w, cudaStream_t st) {
+    SideStream* ss = side_for_current_device();
+    if (!ss) return SFA_ERR_CUDA;
+    const long long L = s->L, Q = s->Q, T = s->T, F = s->F;
+    const int Cd = s->Cd;
+    const long long LQ = L * p.Qp;
+    const float2* G = reinterpret_cast<const float2*>(w + p.off_G);
+    float* Aslab[2] = {reinterpret_cast<float*>(w + p.off_A), reinterpret_cast<float*>(w + p.off_A + p.a_slab)};
+    SFA_CUDA_CHECK(cudaEventRecord(ss->fork, st));               // G is ready / earlier work ordered
+    SFA_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+    int slot = 0;
+    long long it = 0;
+    for (long long f0 = 0; f0 < F; f0 += p.fc, ++it, slot ^= 1) {
+        const long long nf = (F - f0 < p.fc) ? (F - f0) : p.fc;
+        if (it >= 2) SFA_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->done[slot], 0));
+        for (long long g0 = 0; g0 < nf; g0 += 64) {
+            const int ng = (int)((nf - g0 < 64) ? nf - g0 : 64);
+            int rc = launch_steer_build(G, dd + f0 * Cd, Cd, g0, ng, LQ, is_hybrid(s), Aslab[slot] + g0 * 4 * LQ, ss->stream);
+            if (rc != SFA_OK) return rc;
+        }
+        SFA_CUDA_CHECK(cudaEventRecord(ss->built[slot], ss->stream));
+        SFA_CUDA_CHECK(cudaStreamWaitEvent(st, ss->built[slot], 0));
+        int rc = cgemm_splitk(nf, L, T, Q, Aslab[slot], p.Qp, 0, x + f0 * Q * T, T, Q * T, o + f0 * L * T, T, L * T,
+                              nullptr, 0, is_hybrid(s), st);
+        if (rc != SFA_OK) return rc;
+        SFA_CUDA_CHECK(cudaEventRecord(ss->done[slot], st));
+    }
+    return SFA_OK;
+}
+
+static inline size_t elem_bytes(const sfa_pwd_shape* s) { return is_c64(s) ? 8 : 16; }
 
 }  // namespace sfa
 
@@ -473,6 +564,8 @@ extern "C" int sfa_pwd_apply(const sfa_pwd_shape* s, const sfa_c128* Y_L, const 
     rc = pwd_prepare(s, p, yl, reinterpret_cast<const double2*>(Y_Q), w, st);
     if (rc != SFA_OK) return rc;
     const size_t eb = elem_bytes(s);
+    if (is_c64(s) && p.form == 1 && s->F > p.fc)
+        return pwd_steering_pipelined(s, p, dd, reinterpret_cast<const float2*>(X), reinterpret_cast<float2*>(out), w, st);
     for (long long f0 = 0; f0 < s->F; f0 += p.fc) {
         const long long nf = (s->F - f0 < p.fc) ? (s->F - f0) : p.fc;
         rc = pwd_run_bins(s, p, nf, yl, dd + f0 * s->Cd,
@@ -613,11 +706,11 @@ extern "C" int sfa_pwd_host_destroy(sfa_pwd_host_ctx* c) {
 extern "C" int sfa_cgemm3x(int64_t B, int64_t Nn, int64_t Mm, int64_t K, const sfa_c64* P, int64_t ldP,
                            int64_t strideP, const sfa_c64* R, int64_t ldR, int64_t strideR, sfa_c64* out,
                            int64_t ldo, int64_t strideO, const sfa_c64* rowscale, int64_t strideS,
-                           void* stream);
+                           int hybrid, void* stream);
 
 namespace sfa {
 __global__ void split_planar_c64_kernel(const float2* __restrict__ S, long long ld, long long strideB,
-                                        long long batches, long long Nn, long long K, long long Kp,
+                                        long long batches, long long Nn, long long K, long long Kp, int hybrid,
                                         float* __restrict__ P) {
     const long long plane = Nn * Kp;
     const long long total = batches * plane;
@@ -631,8 +724,8 @@ __global__ void split_planar_c64_kernel(const float2* __restrict__ S, long long 
         const float hr = __uint_as_float(tf32_rna(v.x)), hi = __uint_as_float(tf32_rna(v.y));
         o[0] = hr;
         o[plane] = hi;
-        o[2 * plane] = v.x - hr;
-        o[3 * plane] = v.y - hi;
+        o[2 * plane] = hybrid ? pack_bf16_lo_hi(hr, v.x - hr) : v.x - hr;
+        o[3 * plane] = hybrid ? pack_bf16_lo_hi(hi, v.y - hi) : v.y - hi;
     }
 }
 }  // namespace sfa
@@ -640,7 +733,7 @@ __global__ void split_planar_c64_kernel(const float2* __restrict__ S, long long 
 extern "C" int sfa_cgemm3x(int64_t B, int64_t Nn, int64_t Mm, int64_t K, const sfa_c64* P, int64_t ldP,
                            int64_t strideP, const sfa_c64* R, int64_t ldR, int64_t strideR, sfa_c64* out,
                            int64_t ldo, int64_t strideO, const sfa_c64* rowscale, int64_t strideS,
-                           void* stream) {
+                           int hybrid, void* stream) {
     if (B < 0 || Nn < 0 || Mm < 0 || K <= 0) return SFA_ERR_INVALID;
     if (B == 0 || Nn == 0 || Mm == 0) return SFA_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -649,13 +742,13 @@ extern "C" int sfa_cgemm3x(int64_t B, int64_t Nn, int64_t Mm, int64_t K, const s
     float* Pp = nullptr;
     SFA_CUDA_CHECK(cudaMallocAsync(&Pp, (size_t)pb * 4 * Nn * Kp * sizeof(float), st));
     split_planar_c64_kernel<<<grid1d(pb * Nn * Kp), 256, 0, st>>>(reinterpret_cast<const float2*>(P), ldP, strideP,
-                                                                   pb, Nn, K, Kp, Pp);
+                                                                   pb, Nn, K, Kp, hybrid, Pp);
     int rc = SFA_OK;
     if (cudaGetLastError() != cudaSuccess) rc = SFA_ERR_CUDA;
     if (rc == SFA_OK)
         rc = cgemm_splitk(B, Nn, Mm, K, Pp, Kp, strideP == 0, reinterpret_cast<const float2*>(R), ldR, strideR,
                           reinterpret_cast<float2*>(out), ldo, strideO, reinterpret_cast<const float2*>(rowscale),
-                          strideS, st);
+                          strideS, hybrid, st);
     cudaFreeAsync(Pp, st);
     return rc;
 }

@@ -19,7 +19,7 @@ import torch
 from .. import _lib
 from ..util import as_complex_tensor, _device_of
 
-PRECISIONS = {"c64": 0, "c128": 1}
+PRECISIONS = {"c64": 0, "c128": 1, "c64_fast": 2}
 FORMS = {"auto": 0, "steering": 1, "factored": 2}
 
 
@@ -50,8 +50,10 @@ def pwd(Y_look, dn, Y_mic, p, precision=None, form="auto", out=None):
     Y_mic : (Q, M) SH/CH matrix at the microphones, already carrying the quadrature
          weights (``Y_p`` in the examples); it enters conjugate-transposed.
     p : (F, Q) or (F, Q, T) microphone spectra.
-    precision : "c64" (tensor cores, 3xTF32, FP32 accumulate; error ~1e-6 normwise) or
-         "c128" (FP64).  Default: from ``p``'s dtype (complex64 -> "c64", else "c128").
+    precision : "c64" (tensor cores, 3xTF32, FP32 accumulate; error ~1e-6 normwise),
+         "c64_fast" (tensor cores, TF32 for hi*hi + one BF16 pass for the hi*lo cross terms: 2/3 of
+         the tensor work, error still ~1e-6 normwise) or "c128" (FP64 on the CUDA cores).
+         Default: from ``p``'s dtype (complex64 -> "c64", else "c128").
     Returns
     -------
     q : (F, L, T) beam outputs (``np.matmul(A, p[:, :, None])`` keeps the T axis, so T=1 for 2-D p).
@@ -62,10 +64,10 @@ def pwd(Y_look, dn, Y_mic, p, precision=None, form="auto", out=None):
         pd = p.dtype if isinstance(p, torch.Tensor) else np.asarray(p).dtype
         precision = "c64" if pd in (torch.complex64, np.complex64) else "c128"
     if precision not in PRECISIONS:
-        raise ValueError("precision must be 'c64' or 'c128'")
+        raise ValueError("precision must be 'c64', 'c64_fast' or 'c128'")
     if form not in FORMS:
         raise ValueError("form must be 'auto', 'steering' or 'factored'")
-    cdtype = torch.complex64 if precision == "c64" else torch.complex128
+    cdtype = torch.complex128 if precision == "c128" else torch.complex64
     Y_look = as_complex_tensor(Y_look, dev)
     Y_mic = as_complex_tensor(Y_mic, dev)
     dn = as_complex_tensor(dn, dev)
@@ -100,7 +102,7 @@ class PwdPlan:
         self.lib = _lib.require_cuda()
         dev = device if device is not None else _device_of(Y_look, dn, Y_mic)
         self.dev = dev
-        self.cdtype = torch.complex64 if precision == "c64" else torch.complex128
+        self.cdtype = torch.complex128 if precision == "c128" else torch.complex64
         self.Y_look = as_complex_tensor(Y_look, dev)
         self.Y_mic = as_complex_tensor(Y_mic, dev)
         dn = as_complex_tensor(dn, dev)
@@ -132,7 +134,7 @@ class PwdHost:
 
     def __init__(self, Y_look, dn, Y_mic, T, precision="c64", form="auto", device=0, chunk_bins=0):
         self.lib = _lib.require_cuda()
-        self.np_dtype = np.complex64 if precision == "c64" else np.complex128
+        self.np_dtype = np.complex128 if precision == "c128" else np.complex64
         Y_look = np.ascontiguousarray(Y_look, dtype=np.complex128)
         Y_mic = np.ascontiguousarray(Y_mic, dtype=np.complex128)
         dn = np.ascontiguousarray(dn, dtype=np.complex128)

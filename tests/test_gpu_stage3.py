@@ -53,6 +53,7 @@ def test_cgemm3x_direct(mic):
     from sfa_numpy_b200 import _lib
     lib = _lib.load()
     rng = np.random.default_rng(3)
+    worst = {0: 0.0, 1: 0.0}
     cases = [(1, 64, 128, 8), (2, 70, 200, 64), (3, 5, 33, 3), (1, 130, 129, 100), (2, 64, 256, 37),
              (1, 200, 1000, 64), (4, 17, 938, 9)]
     for (B, Nn, Mm, K) in cases:
@@ -64,20 +65,23 @@ def test_cgemm3x_direct(mic):
             R = torch.from_numpy(Rn).cuda()
             S = torch.from_numpy(sc).cuda()
             out = torch.full((B, Nn, Mm), float("nan"), dtype=torch.complex64, device="cuda")
-            for use_scale in (False, True):
+            for use_scale, hybrid in ((False, 0), (True, 0), (False, 1), (True, 1)):
                 _lib.check(lib.sfa_cgemm3x(B, Nn, Mm, K, _lib.ptr(P), K, 0 if shared else Nn * K, _lib.ptr(R), Mm,
                                            K * Mm, _lib.ptr(out), Mm, Nn * Mm, _lib.ptr(S) if use_scale else None,
-                                           Nn, _lib.stream_ptr()))
+                                           Nn, hybrid, _lib.stream_ptr()))
                 ref = np.matmul(Pn.astype(np.complex128), Rn.astype(np.complex128))
                 if use_scale:
                     ref = ref * sc[:, :, None].astype(np.complex128)
                 got = cpu(out)
                 assert np.isfinite(got.view(np.float32)).all(), (B, Nn, Mm, K, shared)
                 err = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
-                assert err < 2e-6, "cgemm3x %s shared=%s scale=%s err %.3e" % ((B, Nn, Mm, K), shared, use_scale, err)
+                worst[hybrid] = max(worst[hybrid], err)
+                assert err < (4e-6 if hybrid else 2e-6), "cgemm3x %s shared=%s scale=%s hybrid=%d err %.3e" % (
+                    (B, Nn, Mm, K), shared, use_scale, hybrid, err)
+    print("cgemm3x worst normwise error: 3xTF32 %.2e, TF32+BF16 %.2e" % (worst[0], worst[1]))
 
 
-@pytest.mark.parametrize("precision,tol", [("c128", TOL128), ("c64", TOL64)])
+@pytest.mark.parametrize("precision,tol", [("c128", TOL128), ("c64", TOL64), ("c64_fast", TOL64)])
 @pytest.mark.parametrize("form", ["steering", "factored", "auto"])
 def test_pwd_golden(mic, golden, precision, tol, form):
     g = golden["pwd"]
@@ -110,7 +114,7 @@ def _dot_sph(v, u):
             np.sin(v[0]) * np.sin(v[1]) * np.sin(u[0]) * np.sin(u[1]) + np.cos(v[1]) * np.cos(u[1]))
 
 
-@pytest.mark.parametrize("precision,tol", [("c128", 1e-10), ("c64", TOL64)])
+@pytest.mark.parametrize("precision,tol", [("c128", 1e-10), ("c64", TOL64), ("c64_fast", TOL64)])
 def test_examples_end_to_end(mic, golden, precision, tol):
     """The four reference example scripts, re-run through the GPU API, against the q the
     unmodified scripts produced (fixtures) incl. the SURVEY 4.4 fingerprints."""
@@ -156,7 +160,7 @@ SHAPES = [  # N, Q, L, F, T   (spherical unless N < 0 -> circular of order -N)
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-@pytest.mark.parametrize("precision,tol", [("c128", TOL128), ("c64", TOL64)])
+@pytest.mark.parametrize("precision,tol", [("c128", TOL128), ("c64", TOL64), ("c64_fast", TOL64)])
 def test_pwd_shapes(mic, shape, precision, tol):
     N, Q, L, F, T = shape
     A, R, S = mic.modal.angular, mic.modal.radial, mic.modal.steering
@@ -180,7 +184,7 @@ def test_pwd_shapes(mic, shape, precision, tol):
         dn_ref, _ = O.regularize(1 / O.circular_pw(N, k, 0.1, "open"), 3000, "softclip")
         dcols = dn_ref
         dn, _ = R.regularize(1 / R.circular_pw(N, k, 0.1, "open"), 3000, "softclip")
-    cd = np.complex64 if precision == "c64" else np.complex128
+    cd = np.complex128 if precision == "c128" else np.complex64
     X = (rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(cd)
     ref = O.pwd_factored(Yq_ref, dcols.reshape(F, -1), Yp_ref, X.astype(np.complex128))
     for form in ("steering", "factored"):
@@ -226,8 +230,8 @@ def test_pwd_host_path(mic):
     k = O.wavenumbers(F) + 0.5
     dn_ref, _ = O.regularize(1 / O.spherical_pw(N, k, 0.042, "rigid"), 100, "softclip")
     rng = np.random.default_rng(5)
-    for precision, tol in (("c64", TOL64), ("c128", TOL128)):
-        cd = np.complex64 if precision == "c64" else np.complex128
+    for precision, tol in (("c64", TOL64), ("c64_fast", TOL64), ("c128", TOL128)):
+        cd = np.complex128 if precision == "c128" else np.complex64
         X = (rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(cd)
         ref = O.pwd_factored(Yq_ref, O.repeat_n_m(dn_ref), Yp_ref, X.astype(np.complex128))
         host = S.PwdHost(Yq_ref, dn_ref, Yp_ref, T, precision=precision, chunk_bins=8)
@@ -238,3 +242,31 @@ def test_pwd_host_path(mic):
         q2 = host(X)                     # pageable memory works too
         assert np.array_equal(q, q2)
         host.close()
+
+
+@pytest.mark.parametrize("precision", ["c64", "c64_fast", "c128"])
+def test_pwd_many_chunks(mic, monkeypatch, precision):
+    """Force a tiny per-chunk scratch budget so the bins are processed in many chunks (for the
+    steering form this is the side-stream pipeline build(i+1) || gemm(i)); results must not change."""
+    import torch
+    A, R, S = mic.modal.angular, mic.modal.radial, mic.modal.steering
+    N, Q, L, F, T = 4, 36, 150, 90, 200
+    az, co, w = O.fibonacci_grid(Q)
+    azl, col, _ = O.fibonacci_grid(L)
+    Y_p, Y_q = A.sht_matrix(N, az, co, w), A.sht_matrix(N, azl, col)
+    k = O.wavenumbers(F) + 0.3
+    _, dn, _ = R.radial_filters(N, k, 0.042, "rigid", 100.0, "softclip")
+    cd = torch.complex128 if precision == "c128" else torch.complex64
+    g = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.randn((F, Q, T), dtype=cd, device="cuda", generator=g)
+    for form in ("steering", "factored"):
+        monkeypatch.delenv("SFA_PWD_CHUNK_MB", raising=False)
+        q_one = S.pwd(Y_q, dn, Y_p, X, precision=precision, form=form)
+        monkeypatch.setenv("SFA_PWD_CHUNK_MB", "0.5")
+        q_many = S.pwd(Y_q, dn, Y_p, X, precision=precision, form=form)
+        torch.cuda.synchronize()
+        assert torch.equal(q_one, q_many), form
+    Yp_ref, Yq_ref = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
+    dn_ref, _ = O.regularize(1 / O.spherical_pw(N, k, 0.042, "rigid"), 100, "softclip")
+    ref = O.pwd_factored(Yq_ref, O.repeat_n_m(dn_ref), Yp_ref, cpu(X).astype(np.complex128))
+    assert bin_err(cpu(q_many), ref) < (TOL128 if precision == "c128" else TOL64)

@@ -10,6 +10,7 @@ import sfa_numpy_b200 as micarray            # noqa: E402
 from oracle import sfa_oracle as O           # noqa: E402  (input generator only)
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 74
+PREC = sys.argv[2] if len(sys.argv) > 2 else "c64"
 N, L, T = 8, 2562, 938
 azi, colat, w = O.grid_equal_angle(3)
 azl, col, _ = O.fibonacci_grid(L)
@@ -19,7 +20,7 @@ Y_p = A.sht_matrix(N, azi, colat, w)
 Y_q = A.sht_matrix(N, azl, col)
 _, dn, _ = R.radial_filters(N, k, 0.042, "rigid", 100.0, "Tikh")
 X = torch.from_numpy(O.synth_spectra(F, 64, T, seed=0)).cuda()
-plan = S.PwdPlan(Y_q, dn, Y_p, T)
+plan = S.PwdPlan(Y_q, dn, Y_p, T, precision=PREC)
 out = torch.empty((F, L, T), dtype=torch.complex64, device="cuda")
 for _ in range(3):
     plan(X, out=out)
@@ -29,4 +30,4 @@ e0.record()
 plan(X, out=out)
 e1.record()
 torch.cuda.synchronize()
-print("F=%d: %.3f ms -> %.3e outputs/s" % (F, e0.elapsed_time(e1), F * L * T / e0.elapsed_time(e1) * 1e3))
+print(PREC, "F=%d: %.3f ms -> %.3e outputs/s" % (F, e0.elapsed_time(e1), F * L * T / e0.elapsed_time(e1) * 1e3))
