@@ -20,7 +20,7 @@
 // (doc/examples/modal_beamforming_rigid_spherical_array.py:38-39), for which
 // pwd_apply.cu issues one or two calls of this kernel per frequency chunk.
 //
-// Mapping onto the machine (one persistent CTA per SM, 320 threads):
+// Mapping onto the machine (one persistent CTA per SM, 448 threads):
 //   * UMMA M (128 TMEM lanes) = 128 consecutive m (time frames) of one batch b.
 //     The R^T tile [128 m x K<=64] is the A operand and lives in TENSOR MEMORY
 //     (TS-form tcgen05.mma): four "loader" warps read R straight from global
@@ -35,11 +35,13 @@
 //   * One elected thread issues the tcgen05.mma.kind::tf32 stream:
 //     3 passes x 4 real products x K/8 k-steps per n-tile, accumulating into a
 //     double-buffered pair of TMEM accumulators (Re, Im: 64 columns each).
-//   * Four epilogue warps read the accumulators with tcgen05.ld (lane = m) and
-//     store complex64 directly: a warp writes 32 consecutive m of one row n =
-//     256 contiguous bytes per store instruction, no shared-memory transpose.
+//   * Eight epilogue warps read the accumulators with tcgen05.ld (lane = m, 32 columns
+//     per warp), release the accumulator at once and store complex64 directly: a warp
+//     writes 32 consecutive m of one row n = 256 contiguous bytes per store instruction,
+//     no shared-memory transpose.
 // TMEM budget: 2 x (64 Re + 64 Im) accumulator columns + 256 operand columns = 512.
 #include <cuda.h>
+#include <stdlib.h>
 #include "sfa_common.cuh"
 
 namespace sfa {
@@ -51,7 +53,8 @@ constexpr int kStagesB = 3;
 constexpr int kBoxK = 32;            // fp32 per 128-byte swizzle row
 constexpr int kBoxBytes = kTileN * kBoxK * 4;            // 8 KB
 constexpr int kStageBytes = 4 * 2 * kBoxBytes;           // 4 planes x 2 k-boxes = 64 KB
-constexpr int kThreads = 320;
+constexpr int kThreads = 480;          // TMA, MMA(Re), 4 loader warps, 8 epilogue warps, MMA(Im)
+constexpr int kImIssuerWarp = 14;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 2 * kTileN;                     // Re + Im per accumulator stage
 constexpr int kOperandCol0 = 2 * kAccCols;               // 256
@@ -72,6 +75,7 @@ struct GemmParams {
     int m_tiles;            // ceil(Mm / 128)
     long long tasks;        // B * m_tiles
     int n_tiles;            // ceil(Nn / 64)
+    int debug_no_tma;
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -242,14 +246,14 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStagesB; ++s) {
             mbar_init(&bars->b_full[s], 1);
-            mbar_init(&bars->b_empty[s], 1);
+            mbar_init(&bars->b_empty[s], 2);      // both MMA issuers commit
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&bars->acc_full[a], 1);
-            mbar_init(&bars->acc_empty[a], 4);
+            mbar_init(&bars->acc_full[a], 2);
+            mbar_init(&bars->acc_empty[a], 8);
         }
         mbar_init(&bars->a_full, 4);
-        mbar_init(&bars->a_empty, 1);
+        mbar_init(&bars->a_empty, 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -275,6 +279,14 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
                 for (int nt = 0; nt < prm.n_tiles; ++nt) {
                     mbar_wait(&bars->b_empty[stage], phase ^ 1);
                     unsigned char* dst = stage_base + (size_t)stage * kStageBytes;
+                    if (prm.debug_no_tma) {              // DEBUG: operand tiles not fetched (timing experiments only)
+                        mbar_arrive(&bars->b_full[stage]);
+                        if (++stage == kStagesB) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&bars->b_full[stage], (uint32_t)(4 * kboxes * kBoxBytes));
 #pragma unroll
                     for (int pl = 0; pl < 4; ++pl) {
@@ -291,8 +303,12 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (whole warp waits, one elected lane issues) =====================
+    } else if (warp == 1 || warp == kImIssuerWarp) {
+        // ===================== MMA issuers (whole warp waits, one elected lane issues) =====================
+        // Two warps share the issue work -- warp 1 feeds the Re accumulator, warp 14 the Im accumulator --
+        // because one thread needs ~45 cycles of descriptor arithmetic per tcgen05.mma while an
+        // M128 x N64 x K8 MMA occupies the tensor pipe for only 32.
+        const bool im_part = (warp == kImIssuerWarp);
         // the last n-tile may be narrow: issue it with UMMA N = remaining rows rounded up to 16
         const int n_tail = (int)(prm.Nn - (long long)(prm.n_tiles - 1) * kTileN);
         const int n_tail16 = ((n_tail + 15) >> 4) << 4;
@@ -334,15 +350,21 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
                                 const uint32_t a_im = a0 + (ap + 1) * kMaxK + ks * 8;
                                 const uint32_t accum = (pass == 0 && ks == 0) ? 0u : 1u;
                                 if (bf) {
-                                    umma_bf16_ts(d_re, a_re, b_re, idesc_bf, accum);
-                                    umma_bf16_ts(d_im, a_re, b_im, idesc_bf, accum);
-                                    umma_bf16_ts(d_re, a_im, b_im, idesc_bf_neg, 1u);
-                                    umma_bf16_ts(d_im, a_im, b_re, idesc_bf, 1u);
+                                    if (!im_part) {
+                                        umma_bf16_ts(d_re, a_re, b_re, idesc_bf, accum);
+                                        umma_bf16_ts(d_re, a_im, b_im, idesc_bf_neg, 1u);
+                                    } else {
+                                        umma_bf16_ts(d_im, a_re, b_im, idesc_bf, accum);
+                                        umma_bf16_ts(d_im, a_im, b_re, idesc_bf, 1u);
+                                    }
                                 } else {
-                                    umma_tf32_ts(d_re, a_re, b_re, idesc, accum);
-                                    umma_tf32_ts(d_im, a_re, b_im, idesc, accum);
-                                    umma_tf32_ts(d_re, a_im, b_im, idesc_neg, 1u);
-                                    umma_tf32_ts(d_im, a_im, b_re, idesc, 1u);
+                                    if (!im_part) {
+                                        umma_tf32_ts(d_re, a_re, b_re, idesc, accum);
+                                        umma_tf32_ts(d_re, a_im, b_im, idesc_neg, 1u);
+                                    } else {
+                                        umma_tf32_ts(d_im, a_re, b_im, idesc, accum);
+                                        umma_tf32_ts(d_im, a_im, b_re, idesc, 1u);
+                                    }
                                 }
                             }
                         }
@@ -422,7 +444,9 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
         // lane = m: one store instruction of a warp writes 32 consecutive complex64 of row n
         // (256 contiguous bytes).  The column loop is kept to a pointer bump + store per value;
         // mode / row-scale / ragged-tile variants are hoisted out of it.
+        // Eight warps: warp w and w+4 share TMEM lane quarter (w & 3) and take 32 columns each.
         const int quarter = warp & 3;
+        const int chalf = (warp - 6) >> 2;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -431,68 +455,85 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
             const int mt = (int)(task - b * prm.m_tiles);
             const long long m = (long long)mt * kTileM + quarter * 32 + lane;
             const bool m_ok = m < prm.Mm;
+            const bool all_ok = __all_sync(0xffffffffu, m_ok);   // false only in a ragged last m-tile
             float2* const out_bm = reinterpret_cast<float2*>(prm.out) + b * prm.strideO + (m_ok ? m : 0);
             const float2* const scale_b = prm.rowscale ? prm.rowscale + b * prm.strideS : nullptr;
             for (int nt = 0; nt < prm.n_tiles; ++nt) {
                 mbar_wait(&bars->acc_full[acc], acc_phase);
                 tcgen05_fence_after();
-                const uint32_t t_re = tmem + lane_base + acc * kAccCols;
-                const long long n0 = (long long)nt * kTileN;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t re[32], im[32];
-                    SFA_TMEM_LD32(t_re + half * 32, re);
-                    SFA_TMEM_LD32(t_re + kTileN + half * 32, im);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (half == 1) {
-                        // accumulator fully read -> hand it back to the MMA warp before storing
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
-                    }
-                    const long long nbase = n0 + half * 32;
-                    long long left = prm.Nn - nbase;
-                    const int ncols = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
-                    if (!m_ok || ncols == 0) continue;
-                    float2* o = out_bm + nbase * prm.ldo;
-                    if (scale_b) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (j < ncols) {
-                                const float2 sc = __ldg(scale_b + nbase + j);
-                                const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
-                                re[j] = __float_as_uint(xr * sc.x - xi * sc.y);
-                                im[j] = __float_as_uint(xr * sc.y + xi * sc.x);
-                            }
-                        }
-                    }
-                    if (prm.out_mode == OUT_C64_ACCUM) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (j < ncols) {
-                                const float2 old = o[(long long)j * prm.ldo];
-                                re[j] = __float_as_uint(__uint_as_float(re[j]) + old.x);
-                                im[j] = __float_as_uint(__uint_as_float(im[j]) + old.y);
-                            }
-                        }
-                    }
-                    if (ncols == 32) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            *o = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
-                            o += prm.ldo;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (j < ncols) *o = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
-                            o += prm.ldo;
-                        }
-                    }
-                }
+                const uint32_t t_re = tmem + lane_base + acc * kAccCols + chalf * 32;
+                uint32_t re[32], im[32];
+                SFA_TMEM_LD32(t_re, re);
+                SFA_TMEM_LD32(t_re + kTileN, im);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // this warp's part of the accumulator is in registers -> release it before storing
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
+                }
+                const long long nbase = (long long)nt * kTileN + chalf * 32;
+                const long long left = prm.Nn - nbase;
+                const int ncols = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+                if (ncols == 0 || prm.out_mode == 99) continue;          // warp-uniform
+                if (!all_ok && !m_ok) continue;                           // ragged m-tile: scalar path, no shuffles
+                float2* o = out_bm + nbase * prm.ldo;
+                long long ldo_eff = prm.ldo;
+                if (scale_b) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < ncols) {
+                            const float2 sc = __ldg(scale_b + nbase + j);
+                            const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
+                            re[j] = __float_as_uint(xr * sc.x - xi * sc.y);
+                            im[j] = __float_as_uint(xr * sc.y + xi * sc.x);
+                        }
+                    }
+                }
+                if (prm.out_mode == OUT_C64_ACCUM) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < ncols) {
+                            const float2 old = o[(long long)j * prm.ldo];
+                            re[j] = __float_as_uint(__uint_as_float(re[j]) + old.x);
+                            im[j] = __float_as_uint(__uint_as_float(im[j]) + old.y);
+                        }
+                    }
+                }
+                // Full tiles with 16-byte aligned rows: lane pairs swap one value per column pair so that
+                // every lane owns two adjacent frames of one row -> 16-byte stores, half as many store
+                // instructions in flight for the same bytes (the LSU store queue is what limits here).
+                const bool vec_ok = all_ok && (ncols == 32) && ((ldo_eff & 1) == 0) &&
+                                    __all_sync(0xffffffffu, (((size_t)o) & 15) == ((lane & 1) ? 8u : 0u));
+                if (vec_ok) {
+                    const bool odd = lane & 1;
+                    float2* ov = odd ? (o + ldo_eff - 1) : o;       // odd lanes own row j+1, frames (t-1, t)
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const uint32_t sr = odd ? re[j] : re[j + 1];
+                        const uint32_t si = odd ? im[j] : im[j + 1];
+                        const uint32_t gr = __shfl_xor_sync(0xffffffffu, sr, 1);
+                        const uint32_t gi = __shfl_xor_sync(0xffffffffu, si, 1);
+                        float4 v;
+                        if (odd) v = make_float4(__uint_as_float(gr), __uint_as_float(gi), __uint_as_float(re[j + 1]), __uint_as_float(im[j + 1]));
+                        else v = make_float4(__uint_as_float(re[j]), __uint_as_float(im[j]), __uint_as_float(gr), __uint_as_float(gi));
+                        *reinterpret_cast<float4*>(ov) = v;
+                        ov += 2 * ldo_eff;
+                    }
+                } else if (ncols == 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        *o = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+                        o += ldo_eff;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < ncols) *o = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+                        o += ldo_eff;
+                    }
                 }
             }
         }
@@ -560,7 +601,8 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     prm.strideO = strideO;
     prm.rowscale = rowscale;
     prm.strideS = strideS;
-    prm.out_mode = out_mode;
+    prm.out_mode = getenv("SFA_DEBUG_NOSTORE") ? 99 : out_mode;
+    prm.debug_no_tma = getenv("SFA_DEBUG_NOTMA") ? 1 : 0;
     prm.m_tiles = (int)ceil_div(Mm, kTileM);
     prm.tasks = B * prm.m_tiles;
     prm.n_tiles = (int)ceil_div(Nn, kTileN);

@@ -25,9 +25,17 @@ out = torch.empty((F, L, T), dtype=torch.complex64, device="cuda")
 for _ in range(3):
     plan(X, out=out)
 torch.cuda.synchronize()
+import ctypes
+from sfa_numpy_b200 import _lib
+lib = _lib.load()
+lib.sfa_prof_enable(1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 plan(X, out=out)
 e1.record()
 torch.cuda.synchronize()
+tot, cnt = ctypes.c_double(), ctypes.c_longlong()
+lib.sfa_prof_read(ctypes.byref(tot), ctypes.byref(cnt))
+lib.sfa_prof_enable(0)
+print("  gemm kernels: %d launches, %.3f ms total" % (cnt.value, tot.value))
 print(PREC, "F=%d: %.3f ms -> %.3e outputs/s" % (F, e0.elapsed_time(e1), F * L * T / e0.elapsed_time(e1) * 1e3))
