@@ -35,6 +35,10 @@ CFG = dict(name="cfg3: rigid sphere N=8, 64 mics (grid_equal_angle(3)), F=1024 b
            N=8, F=1024, L=2562, T=938, r=0.042, a0=100.0, method="Tikh", setup="rigid")
 
 
+DTYPE_NOTE = {"c64": "c64 (3xTF32 on tcgen05, FP32 accumulate; stages 1-2 in f64)",
+              "c64_fast": "c64 (TF32 hi*hi + BF16 cross terms on tcgen05, FP32 accumulate; stages 1-2 in f64)"}
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -180,6 +184,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--precision", default="c64_fast", choices=["c64", "c64_fast"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -219,9 +224,9 @@ def main():
     def step():
         Y_p = A.sht_matrix(N, d_azi, d_col, d_w)
         Y_q = A.sht_matrix(N, d_azl, d_coll)
-        _, dn, _ = R.radial_filters(N, d_k, cfg["r"], cfg["setup"], cfg["a0"], cfg["method"])
+        _, dn, _ = R.radial_filters(N, d_k, cfg["r"], cfg["setup"], cfg["a0"], cfg["method"], check="defer")
         if "p" not in plan:
-            plan["p"] = S.PwdPlan(Y_q, dn, Y_p, T)
+            plan["p"] = S.PwdPlan(Y_q, dn, Y_p, T, precision=args.precision)
         p = plan["p"]
         p.Y_look, p.Y_mic, p.dn = Y_q, Y_p, dn
         return p(X, out=out)
@@ -246,6 +251,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    R.check_deferred()
     launches = lib.sfa_launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -269,7 +275,7 @@ def main():
     alg_flops = 8.0 * F * L * Q * T
     peaks, peak_src = load_peaks()
     achieved = alg_bytes / (gemm_ms_per_step * 1e-3) / 1e9
-    roofline = {"kernel": "cgemm3x_kernel (tcgen05 3xTF32 steering GEMM)", "bound": "hbm",
+    roofline = {"kernel": "cgemm3x_kernel<%s> (tcgen05 steering GEMM)" % ("hybrid" if args.precision == "c64_fast" else "3xTF32"), "bound": "hbm",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None,
                 "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
@@ -279,7 +285,7 @@ def main():
 
     line = {"metric": "beam outputs/sec", "value": value, "unit": "outputs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64 (3xTF32, FP32 accumulate)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NOTE[args.precision],
             "data": "synthetic",
             "config": {"workload": cfg["name"], "bins_per_gpu": F, "outputs_per_step_per_gpu": F * L * T,
                        "l2": "inputs+outputs (20 GB) far larger than L2; no flush needed",
@@ -295,7 +301,7 @@ def main():
             dn_h = R.radial_filters(N, d_k, cfg["r"], cfg["setup"], cfg["a0"], cfg["method"])[1].cpu().numpy()
             del out
             torch.cuda.empty_cache()
-            host = S.PwdHost(Yq_h, dn_h, Yp_h, T, device=local, chunk_bins=0)
+            host = S.PwdHost(Yq_h, dn_h, Yp_h, T, precision=args.precision, device=local, chunk_bins=0)
             Xp = host.pinned_empty((F, Q, T))
             Xp[...] = Xh
             outp = host.pinned_empty((F, L, T))

@@ -55,6 +55,13 @@ SFA_HD c128 cdiv(c128 a, c128 b) {
     const double scl = 1.0 / (b.im + b.re * rat);
     return mk((a.re * rat + a.im) * scl, (a.im * rat - a.re) * scl);
 }
+// |z| < t with np.abs semantics (hypot), without paying for hypot unless z is borderline.
+SFA_HD bool cabs_less(c128 a, double t) {
+    const double m = fmax(fabs(a.re), fabs(a.im));
+    if (!(m < t)) return false;                  // hypot >= max component (also catches NaN)
+    if (m < 0.70710678 * t) return true;         // hypot <= sqrt(2) * max component
+    return hypot(a.re, a.im) < t;
+}
 // exact powers of i (radial.py:67,348: (1j)**n on an integer array), any sign of n
 SFA_HD c128 mul_i_pow(c128 z, int n) {
     switch (((n % 4) + 4) % 4) {
@@ -124,11 +131,14 @@ SFA_HD void sph_jn_array(int nmax, double x, dvec j) {
         }
         return;
     }
-    // backward: f_{n-1} = (2n+1)/x f_n - f_{n+1}
+    // backward: f_{n-1} = (2n+1)/x f_n - f_{n+1};  c = (2n+1)/x is kept as a running double
     int n = miller_start(nmax < 1 ? 1 : nmax, x);
     double fp = 0.0, f = 1.0e-30;
+    double cf = (2 * n + 1) * ix;
+    const double dcf = 2.0 * ix;
     for (; n > nmax + 1; --n) {
-        const double t = (2 * n + 1) * ix * f - fp;
+        const double t = cf * f - fp;
+        cf -= dcf;
         fp = f;
         f = t;
         if (fabs(f) > kRescaleHi) {
@@ -141,7 +151,7 @@ SFA_HD void sph_jn_array(int nmax, double x, dvec j) {
     // scale by rescaling the already stored part when we rescale (rare: only
     // for tiny x), which keeps the code branch-light in the common case.
     for (; n >= 1; --n) {
-        const double t = (2 * n + 1) * ix * f - fp;   // f_{n-1}
+        const double t = (2 * n + 1) * ix * f - fp;   // f_{n-1}  (exact coefficient in the stored range)
         fp = f;
         f = t;
         if (n - 1 <= nmax) j[n - 1] = f;
@@ -215,7 +225,7 @@ SFA_HD void cyl_jn_array(int nmax, double x, dvec J, double* Y0, double* Y1) {
             sum_y1 += ((k & 1) ? -f : f) * w;
         }
         if (n <= nmax) J[n] = f;
-        const double t = n * ix2 * f - fp;   // f_{n-1}
+        const double t = (double)n * ix2 * f - fp;   // f_{n-1}
         fp = f;
         f = t;
         if (fabs(f) > kRescaleHi) {
@@ -245,12 +255,48 @@ SFA_HD void cyl_jn_array(int nmax, double x, dvec J, double* Y0, double* Y1) {
 // dn*hn is NumPy's full complex multiply in both cases (a real hn is upcast to
 // hn+0j), which is what produces NaN for inf*0.
 // ---------------------------------------------------------------------------
-enum RegMethod { REG_NONE = 0, REG_DISCARD = 1, REG_HARDCLIP = 2, REG_SOFTCLIP = 3, REG_TIKH = 4, REG_WNG = 5 };
 
 SFA_HD double tikh_alpha(double a0) {
     const double a = sqrt(a0 / 2.0);
     const double s = sqrt(1.0 - 1.0 / (a * a));
     return (1.0 - s) / (1.0 + s);
+}
+
+enum RegMethod { REG_NONE = 0, REG_DISCARD = 1, REG_HARDCLIP = 2, REG_SOFTCLIP = 3, REG_TIKH = 4, REG_WNG = 5 };
+
+// d = 1/b and |d|^2 in one go.  In the range where b.re^2 + b.im^2 can neither overflow nor lose
+// bits to underflow this is conj(b)/|b|^2 (one division); otherwise NumPy's Smith division and
+// hypot, so that the Inf/NaN/underflow behaviour of the reference is reproduced exactly.
+SFA_HD void reciprocal_mag2(c128 b, c128* d, double* dmag2, bool* fast) {
+    const double m = fmax(fabs(b.re), fabs(b.im));
+    if (m > 1e-140 && m < 1e140) {
+        const double inv = 1.0 / (b.re * b.re + b.im * b.im);
+        *d = mk(b.re * inv, -b.im * inv);
+        *dmag2 = inv;
+        *fast = true;
+    } else {
+        *d = cdiv(mk(1.0, 0.0), b);
+        *dmag2 = 0.0;
+        *fast = false;
+    }
+}
+
+SFA_HD void regularize_one(c128 dn, double a0, int method, double alpha, c128* dn_out, double* hn_out);
+
+// regularize(1/b) with the fast reciprocal when it is safe
+SFA_HD void regularize_inverse(c128 b, double a0, int method, double alpha, c128* dn_out, double* hn_out) {
+    c128 d;
+    double m2;
+    bool fast;
+    reciprocal_mag2(b, &d, &m2, &fast);
+    if (fast && (method == REG_TIKH || method == REG_WNG || method == REG_NONE)) {
+        const double h = (method == REG_TIKH) ? 1.0 / (1.0 + (alpha * alpha) * m2)
+                         : (method == REG_WNG ? 1.0 / m2 : 1.0);
+        *hn_out = h;
+        *dn_out = cmul(d, mk(h, 0.0));
+        return;
+    }
+    regularize_one(d, a0, method, alpha, dn_out, hn_out);
 }
 
 SFA_HD void regularize_one(c128 dn, double a0, int method, double alpha, c128* dn_out, double* hn_out) {

@@ -27,7 +27,7 @@ struct TileOut {
     __device__ __forceinline__ void operator()(int c, c128 v) const { row[c] = make_double2(v.re, v.im); }
 };
 
-__device__ __forceinline__ bool is_zero_entry(double2 v) { return hypot(v.x, v.y) < kZeroThreshold; }
+__device__ __forceinline__ bool is_zero_entry(double2 v) { return cabs_less(mk(v.x, v.y), kZeroThreshold); }
 
 // status[0] zero count, [1] unrepairable column, [2] worklist overflow, [3] worklist length
 __global__ void __launch_bounds__(kRadialThreads)
@@ -41,7 +41,7 @@ radial_filter_kernel(int family, int N, long long F, const double* __restrict__ 
     const int Cp = C | 1;                                   // odd row pitch: conflict-free 16 B rows
     const int T = blockDim.x;
     double2* tile = reinterpret_cast<double2*>(smem_raw);   // [T][Cp]
-    double* scratch = reinterpret_cast<double*>(tile + (size_t)T * Cp);   // 2 arrays [(N+3)][T]
+    double* scratch = reinterpret_cast<double*>(tile + (size_t)T * Cp);   // 1 or 2 arrays [(N+3)][T]
     const int tid = threadIdx.x;
     const long long nblk = (F + T - 1) / T;
     for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
@@ -74,7 +74,7 @@ radial_filter_kernel(int family, int N, long long F, const double* __restrict__ 
             if (method >= 0) {
                 c128 d;
                 double h;
-                regularize_one(cdiv(mk(1.0, 0.0), mk(b.x, b.y)), a0, method, alpha, &d, &h);
+                regularize_inverse(mk(b.x, b.y), a0, method, alpha, &d, &h);
                 dn[g] = make_double2(d.re, d.im);
                 if (hn_real) hn_real[g] = h;
                 else hn_cplx[g] = make_double2(h, 0.0);
@@ -260,7 +260,7 @@ extern "C" int sfa_radial_filter(int kind, int N, int64_t F, const double* k, do
     const int C = family ? 2 * N + 1 : N + 1;
     const int Cp = C | 1;
     const int T = kRadialThreads;
-    const size_t smem = (size_t)T * Cp * sizeof(double2) + (size_t)2 * (N + 3) * T * sizeof(double);
+    const size_t smem = (size_t)T * Cp * sizeof(double2) + (size_t)(scale == 2 ? 2 : 1) * (N + 3) * T * sizeof(double);
     if (smem > 220 * 1024) return SFA_ERR_UNSUPPORTED;
     SFA_CUDA_CHECK(cudaFuncSetAttribute(radial_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const double alpha = (method == SFA_REG_TIKH) ? tikh_alpha(a0) : 0.0;

@@ -1,0 +1,81 @@
+"""Frequency-bin sharding across the GPUs of one box (one process per GPU, torch.distributed).
+
+Bins are independent in stage 3 (and in stage 2 apart from the zero-replacement search, which is
+why stage 2 is simply replicated: it is a few MB), so rank r owns the contiguous slab
+``[f0, f1)`` of the F bins, computes ``q[f0:f1]`` with no communication, and the only collective
+is an optional all-gather of the output slabs (NCCL over NVLink on GPUs; gloo in the CPU tests).
+Stage 1 (SH matrices) is recomputed on every rank -- microseconds, cheaper than a broadcast.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bins(F, world_size, rank):
+    """Contiguous, balanced slab [f0, f1) of F bins for `rank` (first F % world ranks get one more)."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("bad rank/world_size")
+    base, extra = divmod(int(F), int(world_size))
+    f0 = rank * base + min(rank, extra)
+    return f0, f0 + base + (1 if rank < extra else 0)
+
+
+def slab_sizes(F, world_size):
+    return [shard_bins(F, world_size, r)[1] - shard_bins(F, world_size, r)[0] for r in range(world_size)]
+
+
+def _default_compute(Y_look, dn, Y_mic, X, **kw):
+    from .modal import steering
+    return steering.pwd(Y_look, dn, Y_mic, X, **kw)
+
+
+def pwd_sharded(Y_look, dn, Y_mic, X, gather=False, group=None, compute=None, **kw):
+    """Plane-wave decomposition with the bins sharded over the ranks of `group`.
+
+    X and dn may be the full [F, ...] arrays (each rank slices its slab) -- pass
+    ``local=True`` in kw-free form by giving arrays whose first axis already equals the slab.
+    Returns the local slab [f1-f0, L, T]; with ``gather=True`` returns the full [F, L, T] on
+    every rank (one all-gather of the slabs, the only collective on the path).
+    """
+    compute = compute or _default_compute
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    F = dn.shape[0]
+    f0, f1 = shard_bins(F, world, rank)
+    X_loc = X[f0:f1] if X.shape[0] == F else X
+    if X_loc.shape[0] != f1 - f0:
+        raise ValueError("X must hold all {} bins or exactly this rank's {} bins".format(F, f1 - f0))
+    q_loc = compute(Y_look, dn[f0:f1], Y_mic, X_loc, **kw)
+    if not gather or world == 1:
+        return q_loc
+    return all_gather_slabs(q_loc, F, group=group)
+
+
+def all_gather_slabs(q_loc, F, group=None):
+    """All-gather of contiguous [F_r, L, T] slabs into [F, L, T] (uneven slabs are padded to the
+    largest slab for the collective and trimmed afterwards)."""
+    world = dist.get_world_size(group)
+    sizes = slab_sizes(F, world)
+    big = max(sizes)
+    tail = tuple(q_loc.shape[1:])
+    if all(s == big for s in sizes):
+        out = torch.empty((F,) + tail, dtype=q_loc.dtype, device=q_loc.device)
+        dist.all_gather_into_tensor(_as_real(out), _as_real(q_loc.contiguous()), group=group)
+        return out
+    padded = torch.zeros((big,) + tail, dtype=q_loc.dtype, device=q_loc.device)
+    padded[: q_loc.shape[0]] = q_loc
+    buf = torch.empty((world * big,) + tail, dtype=q_loc.dtype, device=q_loc.device)
+    dist.all_gather_into_tensor(_as_real(buf), _as_real(padded), group=group)
+    return torch.cat([buf[r * big: r * big + sizes[r]] for r in range(world)], dim=0)
+
+
+def gather_power_map(q_loc, F, group=None):
+    """Frame-averaged beam power map mean_t |q|^2, [F, L] float32, gathered on every rank: the
+    cheap collective when only the map (not the beam signals) is needed downstream."""
+    p_loc = (q_loc.real.float() ** 2 + q_loc.imag.float() ** 2).mean(dim=-1)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return p_loc
+    return all_gather_slabs(p_loc, F, group=group)
+
+
+def _as_real(t):
+    return torch.view_as_real(t) if t.is_complex() else t

@@ -29,7 +29,51 @@ def _method_id(method):
     return _METHODS[method]
 
 
-def _radial(kind, N, k, r, rs, setup, replace_zeros, method=None, a0=0.0):
+class _DeferredChecks:
+    """Zero-replacement status words copied to pinned host memory without stalling the stream.
+    `flush()` (called by the next radial call and by `radial.check_deferred()`) raises the
+    ValueError the reference would have raised (radial.py:209)."""
+
+    def __init__(self):
+        self.pending = []
+
+    def add(self, status):
+        host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+        host.copy_(status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((ev, host))
+
+    def flush(self, wait=False):
+        keep = []
+        for ev, host in self.pending:
+            if not wait and not ev.query():
+                keep.append((ev, host))
+                continue
+            ev.synchronize()
+            _raise_for_status(host.tolist())
+        self.pending = keep
+
+
+_deferred = _DeferredChecks()
+
+
+def check_deferred():
+    """Wait for and validate every deferred zero-replacement status (see `check="defer"`)."""
+    pending, _deferred.pending = _deferred.pending, []
+    for ev, host in pending:
+        ev.synchronize()
+        _raise_for_status(host.tolist())
+
+
+def _raise_for_status(st):
+    if st[1]:
+        raise ValueError("Could not replace zero value in A.")           # radial.py:209
+    if st[2]:
+        raise RuntimeError("sfa_radial_filter: more than 2**20 zero entries to replace")
+
+
+def _radial(kind, N, k, r, rs, setup, replace_zeros, method=None, a0=0.0, check="now"):
     """One launch of sfa_radial_filter.  Returns (bn, dn, hn) un-squeezed ([F, C])."""
     lib = _lib.require_cuda()
     sid = _setup_id(setup)
@@ -52,11 +96,11 @@ def _radial(kind, N, k, r, rs, setup, replace_zeros, method=None, a0=0.0):
                                          int(bool(replace_zeros)), mid, float(a0), _lib.ptr(bn), _lib.ptr(dn),
                                          _lib.ptr(hn), _lib.ptr(status), _lib.ptr(work), _lib.stream_ptr(dev)))
     if replace_zeros:
-        st = status.tolist()
-        if st[1]:
-            raise ValueError("Could not replace zero value in A.")           # radial.py:209
-        if st[2]:
-            raise RuntimeError("sfa_radial_filter: more than 2**20 zero entries to replace")
+        if check == "defer":
+            _deferred.flush()
+            _deferred.add(status)
+        else:
+            _raise_for_status(status.tolist())
     return bn, dn, hn
 
 
@@ -112,15 +156,17 @@ def circular_ls(N, k, r, rs, setup, replace_zeros=True):
     return bn.squeeze()
 
 
-def radial_filters(N, k, r, setup, a0, method, kind="spherical_pw", rs=0.0, replace_zeros=True):
+def radial_filters(N, k, r, setup, a0, method, kind="spherical_pw", rs=0.0, replace_zeros=True, check="now"):
     """Fused ``bn = <kind>(N, k, r, setup); dn, hn = regularize(1/bn, a0, method)`` in ONE kernel
     pass (the inverse never makes a separate trip through HBM).  Returns (bn, dn, hn), squeezed.
-    Equivalent reference sequence: modal_beamforming_rigid_spherical_array.py:34-35."""
+    Equivalent reference sequence: modal_beamforming_rigid_spherical_array.py:34-35.
+    ``check="defer"`` keeps the call asynchronous: the "Could not replace zero value" check is
+    validated later (next radial call or ``check_deferred()``) instead of synchronising now."""
     if kind not in _KINDS:
         raise ValueError("unknown radial function: %r" % (kind,))
     kk = asarray_1d(k)
     bn, dn, hn = _radial(_KINDS[kind], N, kk, r, rs, setup,
-                         replace_zeros and kind not in ("weights", "circ_radial_weights"), method, a0)
+                         replace_zeros and kind not in ("weights", "circ_radial_weights"), method, a0, check)
     return bn.squeeze(), dn.squeeze(), hn.squeeze()
 
 
