@@ -58,6 +58,8 @@ constexpr int kImIssuerWarp = 14;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 2 * kTileN;                     // Re + Im per accumulator stage
 constexpr int kOperandCol0 = 2 * kAccCols;               // 256
+constexpr int kStoreRows = 16;                           // rows (n) per TMA store box
+constexpr int kStoreBytes = kStoreRows * kTileM * 8;     // 16 KB staging buffer per epilogue half
 
 enum OutMode { OUT_C64 = 0, OUT_C64_ACCUM = 2 };
 
@@ -76,6 +78,7 @@ struct GemmParams {
     long long tasks;        // B * m_tiles
     int n_tiles;            // ceil(Nn / 64)
     int debug_no_tma;
+    int tma_store;          // epilogue stages tiles in smem and writes them with TMA (needs even ldo)
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -115,6 +118,21 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+// smem tile -> global through the tensor map (bulk async group); `reduce_add` accumulates (split-K)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2,
+                                             bool reduce_add) {
+    if (reduce_add)
+        asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                     : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                     : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -231,12 +249,14 @@ struct __align__(8) Barriers {
 
 template <bool kHybrid>
 __global__ void __launch_bounds__(kThreads, 1)
-cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) {
+cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant__ CUtensorMap o_map,
+               const GemmParams prm) {
     extern __shared__ unsigned char smem_dyn[];
     // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack.
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char* stage_base = smem;                                    // kStagesB x 64 KB
-    Barriers* bars = reinterpret_cast<Barriers*>(smem + (size_t)kStagesB * kStageBytes);
+    unsigned char* store_base = smem + (size_t)kStagesB * kStageBytes;   // 2 x 16 KB epilogue staging
+    Barriers* bars = reinterpret_cast<Barriers*>(store_base + 2 * kStoreBytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -477,6 +497,43 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
                 const long long nbase = (long long)nt * kTileN + chalf * 32;
                 const long long left = prm.Nn - nbase;
                 const int ncols = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+                if (prm.tma_store) {
+                    // ---- TMEM -> regs -> smem (row = n, 128 frames contiguous) -> TMA store ----
+                    // The four warps of this column half share one 16 KB buffer: 2 x 16 rows per n-tile.
+                    // TMA clips rows >= Nn and frames >= Mm, so ragged tiles need no predicates.
+                    if (prm.out_mode == 99) continue;
+                    if (scale_b) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < ncols) {
+                                const float2 sc = __ldg(scale_b + nbase + j);
+                                const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
+                                re[j] = __float_as_uint(xr * sc.x - xi * sc.y);
+                                im[j] = __float_as_uint(xr * sc.y + xi * sc.x);
+                            }
+                        }
+                    }
+                    float2* sbuf = reinterpret_cast<float2*>(store_base + chalf * kStoreBytes) + quarter * 32 + lane;
+                    const bool issuer = (quarter == 0) && (lane == 0);
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {
+                        // the previous store from this buffer must have finished reading shared memory
+                        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        named_bar_sync(1 + chalf, 128);
+#pragma unroll
+                        for (int j = 0; j < kStoreRows; ++j)
+                            sbuf[j * kTileM] = make_float2(__uint_as_float(re[part * kStoreRows + j]),
+                                                           __uint_as_float(im[part * kStoreRows + j]));
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        named_bar_sync(1 + chalf, 128);
+                        if (issuer && ncols > part * kStoreRows) {
+                            tma_store_3d(&o_map, store_base + chalf * kStoreBytes, 2 * mt * kTileM,
+                                         (int)nbase + part * kStoreRows, (int)b, prm.out_mode == OUT_C64_ACCUM);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                    continue;
+                }
                 if (ncols == 0 || prm.out_mode == 99) continue;          // warp-uniform
                 if (!all_ok && !m_ok) continue;                           // ragged m-tile: scalar path, no shuffles
                 float2* o = out_bm + nbase * prm.ldo;
@@ -539,6 +596,8 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const GemmParams prm) 
         }
     }
 
+    // outstanding bulk stores of this thread (epilogue issuers) must complete before the CTA exits
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -587,7 +646,24 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
         set_last_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
         return SFA_ERR_CUDA;
     }
+    // Output tensor map for the TMA-store epilogue: fp32 view [B][Nn][2*ldo], box = 16 rows x 128 complex.
+    const int tma_store = ((ldo & 1) == 0 && (strideO & 1) == 0 && (((uintptr_t)out) & 15) == 0 &&
+                           !getenv("SFA_NO_TMA_STORE")) ? 1 : 0;
+    CUtensorMap omap = map;
+    if (tma_store) {
+        cuuint64_t odim[3] = {(cuuint64_t)(2 * Mm), (cuuint64_t)Nn, (cuuint64_t)B};
+        cuuint64_t ostr[2] = {(cuuint64_t)ldo * 8, (cuuint64_t)strideO * 8};
+        cuuint32_t obox[3] = {(cuuint32_t)(2 * kTileM), (cuuint32_t)kStoreRows, 1};
+        CUresult r2 = encode(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)out, odim, ostr, obox, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r2 != CUDA_SUCCESS) {
+            set_last_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(out)");
+            return SFA_ERR_CUDA;
+        }
+    }
     GemmParams prm;
+    prm.tma_store = tma_store;
     prm.B = B;
     prm.Nn = Nn;
     prm.Mm = Mm;
@@ -601,12 +677,17 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     prm.strideO = strideO;
     prm.rowscale = rowscale;
     prm.strideS = strideS;
+#ifdef SFA_DEBUG_HOOKS   // timing-attribution experiments only; never compiled into the shipped library
     prm.out_mode = getenv("SFA_DEBUG_NOSTORE") ? 99 : out_mode;
     prm.debug_no_tma = getenv("SFA_DEBUG_NOTMA") ? 1 : 0;
+#else
+    prm.out_mode = out_mode;
+    prm.debug_no_tma = 0;
+#endif
     prm.m_tiles = (int)ceil_div(Mm, kTileM);
     prm.tasks = B * prm.m_tiles;
     prm.n_tiles = (int)ceil_div(Nn, kTileN);
-    const size_t smem = (size_t)kStagesB * kStageBytes + sizeof(Barriers) + 1024;
+    const size_t smem = (size_t)kStagesB * kStageBytes + 2 * kStoreBytes + sizeof(Barriers) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         SFA_CUDA_CHECK(cudaFuncSetAttribute(cgemm3x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -615,8 +696,8 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     }
     long long grid = prm.tasks < sm_count() ? prm.tasks : sm_count();
     prof_begin(st);
-    if (hybrid) cgemm3x_kernel<true><<<(unsigned)grid, kThreads, smem, st>>>(map, prm);
-    else cgemm3x_kernel<false><<<(unsigned)grid, kThreads, smem, st>>>(map, prm);
+    if (hybrid) cgemm3x_kernel<true><<<(unsigned)grid, kThreads, smem, st>>>(map, omap, prm);
+    else cgemm3x_kernel<false><<<(unsigned)grid, kThreads, smem, st>>>(map, omap, prm);
     prof_end(st);
     SFA_LAUNCH_CHECK();
     return SFA_OK;
