@@ -78,6 +78,8 @@ struct GemmParams {
     long long tasks;        // B * m_tiles
     int n_tiles;            // ceil(Nn / 64)
     int debug_no_tma;
+    int csize;              // CTAs per cluster sharing the P stream by TMA multicast (1 or 2)
+    int m_groups;           // ceil(m_tiles / csize)
     int tma_store;          // epilogue stages tiles in smem and writes them with TMA (needs even ldo)
 };
 
@@ -133,6 +135,30 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// multicast variant: one L2 read, the box lands at the same offset in every CTA of `mask`
+// and completes bytes on each destination CTA's mbarrier at the same offset
+__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                               int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+// commit that arrives on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -260,13 +286,20 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // Clusters of `csize` CTAs walk the (batch, m-group) list together: CTA r of a cluster owns
+    // m-tile  mg * csize + r  (a "ghost" tile beyond m_tiles computes zeros and stores nothing).
+    const int csize = prm.csize;
+    const uint32_t crank = (csize > 1) ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+    const long long cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
+    const long long n_groups = prm.B * prm.m_groups;
     const int ksteps = (prm.K + 7) >> 3;               // MMA k-steps of 8
     const int kboxes = (prm.K + kBoxK - 1) / kBoxK;    // TMA boxes along k (1 or 2)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStagesB; ++s) {
             mbar_init(&bars->b_full[s], 1);
-            mbar_init(&bars->b_empty[s], 2);      // both MMA issuers commit
+            mbar_init(&bars->b_empty[s], 2 * csize);   // both MMA issuers of every CTA in the cluster
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->acc_full[a], 2);
@@ -284,6 +317,7 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();                 // peers' barriers are initialised before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
@@ -293,8 +327,8 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
             asm volatile("prefetch.tensormap [%0];" ::"l"(&p_map) : "memory");
             int stage = 0;
             uint32_t phase = 0;
-            for (long long task = blockIdx.x; task < prm.tasks; task += gridDim.x) {
-                const long long b = task / prm.m_tiles;
+            for (long long grp = cluster_id; grp < n_groups; grp += n_clusters) {
+                const long long b = grp / prm.m_groups;
                 const int pb = prm.p_shared ? 0 : (int)b;
                 for (int nt = 0; nt < prm.n_tiles; ++nt) {
                     mbar_wait(&bars->b_empty[stage], phase ^ 1);
@@ -310,11 +344,17 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
                     mbar_arrive_expect_tx(&bars->b_full[stage], (uint32_t)(4 * kboxes * kBoxBytes));
 #pragma unroll
                     for (int pl = 0; pl < 4; ++pl) {
-                        tma_load_3d(&p_map, &bars->b_full[stage], dst + (pl * 2) * kBoxBytes, 0, nt * kTileN,
-                                    pb * 4 + pl);
-                        if (kboxes > 1)
-                            tma_load_3d(&p_map, &bars->b_full[stage], dst + (pl * 2 + 1) * kBoxBytes, kBoxK,
-                                        nt * kTileN, pb * 4 + pl);
+#pragma unroll
+                        for (int kb = 0; kb < 2; ++kb) {
+                            if (kb >= kboxes) continue;
+                            unsigned char* d = dst + (pl * 2 + kb) * kBoxBytes;
+                            if (csize == 1) {
+                                tma_load_3d(&p_map, &bars->b_full[stage], d, kb * kBoxK, nt * kTileN, pb * 4 + pl);
+                            } else if (((kboxes > 1 ? pl * 2 + kb : pl) & 1) == (int)crank) {
+                                // each CTA of the pair fetches half of the boxes and multicasts them to both
+                                tma_load_3d_mc(&p_map, &bars->b_full[stage], d, kb * kBoxK, nt * kTileN, pb * 4 + pl, cmask);
+                            }
+                        }
                     }
                     if (++stage == kStagesB) {
                         stage = 0;
@@ -334,7 +374,7 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
         const int n_tail16 = ((n_tail + 15) >> 4) << 4;
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0, a_phase = 0;
-        for (long long task = blockIdx.x; task < prm.tasks; task += gridDim.x) {
+        for (long long grp = cluster_id; grp < n_groups; grp += n_clusters) {
             mbar_wait(&bars->a_full, a_phase);
             for (int nt = 0; nt < prm.n_tiles; ++nt) {
                 mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
@@ -389,7 +429,8 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
                             }
                         }
                     }
-                    tcgen05_commit(&bars->b_empty[stage]);
+                    if (csize == 1) tcgen05_commit(&bars->b_empty[stage]);
+                    else tcgen05_commit_mc(&bars->b_empty[stage], cmask);   // frees the slot in every CTA of the cluster
                     tcgen05_commit(&bars->acc_full[acc]);
                     if (nt == prm.n_tiles - 1) tcgen05_commit(&bars->a_empty);
                 }
@@ -410,9 +451,9 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may touch
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         uint32_t a_phase = 0;
-        for (long long task = blockIdx.x; task < prm.tasks; task += gridDim.x) {
-            const long long b = task / prm.m_tiles;
-            const int mt = (int)(task - b * prm.m_tiles);
+        for (long long grp = cluster_id; grp < n_groups; grp += n_clusters) {
+            const long long b = grp / prm.m_groups;
+            const int mt = (int)(grp - b * prm.m_groups) * csize + (int)crank;
             const long long m = (long long)mt * kTileM + quarter * 32 + lane;
             const bool m_ok = m < prm.Mm;
             const float2* src = prm.R + b * prm.strideR + (m_ok ? m : 0);
@@ -470,9 +511,9 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (long long task = blockIdx.x; task < prm.tasks; task += gridDim.x) {
-            const long long b = task / prm.m_tiles;
-            const int mt = (int)(task - b * prm.m_tiles);
+        for (long long grp = cluster_id; grp < n_groups; grp += n_clusters) {
+            const long long b = grp / prm.m_groups;
+            const int mt = (int)(grp - b * prm.m_groups) * csize + (int)crank;
             const long long m = (long long)mt * kTileM + quarter * 32 + lane;
             const bool m_ok = m < prm.Mm;
             const bool all_ok = __all_sync(0xffffffffu, m_ok);   // false only in a ragged last m-tile
@@ -600,6 +641,7 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tcgen05_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();                 // no CTA leaves while a peer may still write into it
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
@@ -694,11 +736,33 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
         SFA_CUDA_CHECK(cudaFuncSetAttribute(cgemm3x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    long long grid = prm.tasks < sm_count() ? prm.tasks : sm_count();
+    // CTA pairs share the P stream by TMA multicast whenever a batch has at least two m-tiles.
+    const int csize = (prm.m_tiles >= 2 && !getenv("SFA_NO_CLUSTER")) ? 2 : 1;
+    prm.csize = csize;
+    prm.m_groups = (prm.m_tiles + csize - 1) / csize;
+    const long long n_groups = B * prm.m_groups;
+    const long long max_clusters = sm_count() / csize;
+    const long long grid = (n_groups < max_clusters ? n_groups : max_clusters) * csize;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = csize;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
     prof_begin(st);
-    if (hybrid) cgemm3x_kernel<true><<<(unsigned)grid, kThreads, smem, st>>>(map, omap, prm);
-    else cgemm3x_kernel<false><<<(unsigned)grid, kThreads, smem, st>>>(map, omap, prm);
+    cudaError_t le = hybrid ? cudaLaunchKernelEx(&cfg, cgemm3x_kernel<true>, map, omap, prm)
+                            : cudaLaunchKernelEx(&cfg, cgemm3x_kernel<false>, map, omap, prm);
     prof_end(st);
+    if (le != cudaSuccess) {
+        set_last_cuda_error(le, "cudaLaunchKernelEx(cgemm3x_kernel)");
+        return SFA_ERR_CUDA;
+    }
     SFA_LAUNCH_CHECK();
     return SFA_OK;
 }
