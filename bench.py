@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-stage12", action="store_true")
     ap.add_argument("--precision", default="c64_fast", choices=["c64", "c64_fast"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -319,6 +320,16 @@ def main():
             line["e2e"] = {"value": None, "unit": "outputs/s", "error": repr(e)}
     if rank == 0 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(O, cfg, azi, colat, w, azl, col, k)
+    if rank == 0 and not args.no_stage12:
+        # second half of the BASELINE metric: SH / Bessel evals per second (stages 1 and 2)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_stage12
+            rows = bench_stage12.run(cpu=not args.no_cpu, hbm_gbs=peaks["hbm_gbs"])
+            line["stage12"] = [{k2: (round(v, 6) if isinstance(v, float) and abs(v) < 1e3 else v)
+                                for k2, v in r.items()} for r in rows]
+        except Exception as e:
+            line["stage12"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

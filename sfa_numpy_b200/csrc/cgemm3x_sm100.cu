@@ -53,7 +53,7 @@ constexpr int kStagesB = 3;
 constexpr int kBoxK = 32;            // fp32 per 128-byte swizzle row
 constexpr int kBoxBytes = kTileN * kBoxK * 4;            // 8 KB
 constexpr int kStageBytes = 4 * 2 * kBoxBytes;           // 4 planes x 2 k-boxes = 64 KB
-constexpr int kThreads = 480;          // TMA, MMA(Re), 4 loader warps, 8 epilogue warps, MMA(Im)
+constexpr int kThreads = 480;          // TMA, MMA, 4 loader warps, 8 epilogue warps (+ optional 2nd MMA issuer)
 constexpr int kImIssuerWarp = 14;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 2 * kTileN;                     // Re + Im per accumulator stage
@@ -78,6 +78,7 @@ struct GemmParams {
     long long tasks;        // B * m_tiles
     int n_tiles;            // ceil(Nn / 64)
     int debug_no_tma;
+    int issuers;            // MMA issuer warps per CTA (1 or 2)
     int csize;              // CTAs per cluster sharing the P stream by TMA multicast (1 or 2)
     int m_groups;           // ceil(m_tiles / csize)
     int tma_store;          // epilogue stages tiles in smem and writes them with TMA (needs even ldo)
@@ -299,14 +300,14 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStagesB; ++s) {
             mbar_init(&bars->b_full[s], 1);
-            mbar_init(&bars->b_empty[s], 2 * csize);   // both MMA issuers of every CTA in the cluster
+            mbar_init(&bars->b_empty[s], prm.issuers * csize);   // every MMA issuer of every CTA in the cluster
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&bars->acc_full[a], 2);
+            mbar_init(&bars->acc_full[a], prm.issuers);
             mbar_init(&bars->acc_empty[a], 8);
         }
         mbar_init(&bars->a_full, 4);
-        mbar_init(&bars->a_empty, 2);
+        mbar_init(&bars->a_empty, prm.issuers);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -363,12 +364,12 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1 || warp == kImIssuerWarp) {
+    } else if (warp == 1 || (warp == kImIssuerWarp && prm.issuers == 2)) {
         // ===================== MMA issuers (whole warp waits, one elected lane issues) =====================
-        // Two warps share the issue work -- warp 1 feeds the Re accumulator, warp 14 the Im accumulator --
-        // because one thread needs ~45 cycles of descriptor arithmetic per tcgen05.mma while an
-        // M128 x N64 x K8 MMA occupies the tensor pipe for only 32.
+        // Optionally (SFA_ISSUERS=2) two warps share the issue work: warp 1 feeds the Re accumulator,
+        // warp 14 the Im accumulator.  Measured on B200: no gain, the tensor pipe is not issue-bound.
         const bool im_part = (warp == kImIssuerWarp);
+        const bool both = prm.issuers == 1;            // a single issuer feeds both accumulators
         // the last n-tile may be narrow: issue it with UMMA N = remaining rows rounded up to 16
         const int n_tail = (int)(prm.Nn - (long long)(prm.n_tiles - 1) * kTileN);
         const int n_tail16 = ((n_tail + 15) >> 4) << 4;
@@ -410,18 +411,20 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
                                 const uint32_t a_im = a0 + (ap + 1) * kMaxK + ks * 8;
                                 const uint32_t accum = (pass == 0 && ks == 0) ? 0u : 1u;
                                 if (bf) {
-                                    if (!im_part) {
+                                    if (both || !im_part) {
                                         umma_bf16_ts(d_re, a_re, b_re, idesc_bf, accum);
                                         umma_bf16_ts(d_re, a_im, b_im, idesc_bf_neg, 1u);
-                                    } else {
+                                    }
+                                    if (both || im_part) {
                                         umma_bf16_ts(d_im, a_re, b_im, idesc_bf, accum);
                                         umma_bf16_ts(d_im, a_im, b_re, idesc_bf, 1u);
                                     }
                                 } else {
-                                    if (!im_part) {
+                                    if (both || !im_part) {
                                         umma_tf32_ts(d_re, a_re, b_re, idesc, accum);
                                         umma_tf32_ts(d_re, a_im, b_im, idesc_neg, 1u);
-                                    } else {
+                                    }
+                                    if (both || im_part) {
                                         umma_tf32_ts(d_im, a_re, b_im, idesc, accum);
                                         umma_tf32_ts(d_im, a_im, b_re, idesc, 1u);
                                     }
@@ -745,7 +748,10 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     const long long grid = (n_groups < max_clusters ? n_groups : max_clusters) * csize;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kThreads);
+    // One issuer warp is enough (measured: a second one, splitting Re/Im, changes nothing) and keeps
+    // the CTA at 448 threads x 128 registers, which leaves room for a steering-build CTA on the SM.
+    prm.issuers = (getenv("SFA_ISSUERS") && atoi(getenv("SFA_ISSUERS")) == 2) ? 2 : 1;
+    cfg.blockDim = dim3(prm.issuers == 2 ? kThreads : kThreads - 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr;

@@ -127,36 +127,30 @@ __global__ void group_products_kernel(const double2* __restrict__ YL, const doub
 // slab; every store instruction of a warp writes 128 contiguous bytes of one plane.
 // HBM-store-bound: 16 B out per steering entry.
 template <int NG>
-__global__ void __launch_bounds__(256)
-steer_build_split_kernel(const float2* __restrict__ G, const double2* __restrict__ d, int Cd, int ngroups,
+__global__ void __launch_bounds__(128)
+steer_build_split_kernel(const float2* __restrict__ G, const float2* __restrict__ d, int Cd, int ngroups,
                          long long f0, int nf, long long LQ, int hybrid, float* __restrict__ A) {
-    extern __shared__ float2 sh_d[];                    // [nf][NG], zero padded
-    for (int i = threadIdx.x; i < nf * NG; i += blockDim.x) {
-        const int f = i / NG, g = i - f * NG;
-        float2 v = make_float2(0.f, 0.f);
-        if (g < ngroups) {
-            const double2 dv = d[(f0 + f) * Cd + g];
-            v = make_float2((float)dv.x, (float)dv.y);
-        }
-        sh_d[i] = v;
-    }
-    __syncthreads();
+    // No shared memory and 128 threads: one of these CTAs fits on an SM beside the (persistent)
+    // GEMM CTA, so this kernel really runs under the GEMM of the previous chunk.
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < LQ;
          e += (long long)gridDim.x * blockDim.x) {
         float2 g[NG];
 #pragma unroll
         for (int c = 0; c < NG; ++c) g[c] = (c < ngroups) ? __ldg(G + (long long)c * LQ + e) : make_float2(0.f, 0.f);
         float* o = A + e;
-#pragma unroll 2
         for (int f = 0; f < nf; ++f) {
+            const float2* df = d + (f0 + f) * Cd;           // warp-uniform address: broadcast through L1
             float ar = 0.f, ai = 0.f;
 #pragma unroll
             for (int c = 0; c < NG; ++c) {
-                const float2 dv = sh_d[f * NG + c];
-                ar = fmaf(dv.x, g[c].x, ar);
-                ar = fmaf(-dv.y, g[c].y, ar);
-                ai = fmaf(dv.x, g[c].y, ai);
-                ai = fmaf(dv.y, g[c].x, ai);
+                if (c < ngroups) {
+                    const float2 dd = __ldg(df + c);
+                    const float dx = dd.x, dy = dd.y;
+                    ar = fmaf(dx, g[c].x, ar);
+                    ar = fmaf(-dy, g[c].y, ar);
+                    ai = fmaf(dx, g[c].y, ai);
+                    ai = fmaf(dy, g[c].x, ai);
+                }
             }
             const float hr = __uint_as_float(tf32_rna(ar)), hi = __uint_as_float(tf32_rna(ai));
             __stcs(o, hr);
@@ -168,15 +162,20 @@ steer_build_split_kernel(const float2* __restrict__ G, const double2* __restrict
     }
 }
 
-static int launch_steer_build(const float2* G, const double2* d, int Cd, long long f0, int nf, long long LQ,
+__global__ void d_to_float_kernel(const double2* __restrict__ d, long long n, float2* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = make_float2((float)d[i].x, (float)d[i].y);
+}
+
+static int launch_steer_build(const float2* G, const float2* d, int Cd, long long f0, int nf, long long LQ,
                               int hybrid, float* A, cudaStream_t st) {
-    const unsigned grid = (unsigned)ceil_div(LQ, 256);
+    const unsigned grid = (unsigned)ceil_div(LQ, 128);
     if (Cd <= 16)
-        steer_build_split_kernel<16><<<grid, 256, (size_t)nf * 16 * sizeof(float2), st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
+        steer_build_split_kernel<16><<<grid, 128, 0, st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
     else if (Cd <= 32)
-        steer_build_split_kernel<32><<<grid, 256, (size_t)nf * 32 * sizeof(float2), st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
+        steer_build_split_kernel<32><<<grid, 128, 0, st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
     else
-        steer_build_split_kernel<64><<<grid, 256, (size_t)nf * 64 * sizeof(float2), st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
+        steer_build_split_kernel<64><<<grid, 128, 0, st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
     SFA_LAUNCH_CHECK();
     return SFA_OK;
 }
@@ -307,7 +306,7 @@ struct Plan {
     long long Qp, Mp, Tld;      // padded k extents / leading dims
     int ngroups;
     long long fc;               // bins per chunk
-    size_t off_G, off_A, off_P1, off_P2, off_dcols, off_Z, total, a_slab;
+    size_t off_G, off_A, off_dF, off_P1, off_P2, off_dcols, off_Z, total, a_slab;
 };
 
 static inline bool is_c64(const sfa_pwd_shape* s) {
@@ -358,7 +357,7 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
     if (fc > s->F) fc = s->F > 0 ? s->F : 1;
     p->fc = fc;
     size_t off = 0;
-    p->off_G = p->off_A = p->off_P1 = p->off_P2 = p->off_dcols = p->off_Z = p->a_slab = 0;
+    p->off_G = p->off_A = p->off_dF = p->off_P1 = p->off_P2 = p->off_dcols = p->off_Z = p->a_slab = 0;
     const size_t esz = c64 ? 8 : 16;
     if (form == 1) {
         p->off_G = off;
@@ -366,6 +365,8 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
         p->off_A = off;                                       // two slabs: build(i+1) overlaps gemm(i)
         p->a_slab = align_up((size_t)fc * s->L * p->Qp * 16); // 4 fp32 planes == one complex128
         off += 2 * p->a_slab;
+        p->off_dF = off;                                      // d as complex64 for the build kernel
+        off += align_up((size_t)(s->F > fc ? s->F : fc) * s->Cd * 8);
     } else {
         p->off_P1 = off;
         off += align_up((size_t)s->M * p->Qp * 16);
@@ -438,11 +439,11 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
         if (p.form == 1) {
             const float2* G = reinterpret_cast<const float2*>(w + p.off_G);
             float* A = reinterpret_cast<float*>(w + p.off_A);
-            for (long long g0 = 0; g0 < nf; g0 += 64) {          // d staged through smem, <= 64 bins a time
-                const int ng = (int)((nf - g0 < 64) ? nf - g0 : 64);
-                rc = launch_steer_build(G, dd, Cd, g0, ng, LQ, is_hybrid(s), A + g0 * 4 * LQ, st);
-                if (rc != SFA_OK) return rc;
-            }
+            float2* dF = reinterpret_cast<float2*>(w + p.off_dF);
+            d_to_float_kernel<<<grid1d(nf * Cd), 256, 0, st>>>(dd, nf * Cd, dF);
+            SFA_LAUNCH_CHECK();
+            rc = launch_steer_build(G, dF, Cd, 0, (int)nf, LQ, is_hybrid(s), A, st);
+            if (rc != SFA_OK) return rc;
             return cgemm_splitk(nf, L, T, Q, A, p.Qp, 0, x, T, Q * T, o, T, L * T, nullptr, 0, is_hybrid(s), st);
         }
         const float* P1 = reinterpret_cast<const float*>(w + p.off_P1);
@@ -514,16 +515,18 @@ static int pwd_steering_pipelined(const sfa_pwd_shape* s, const Plan& p, const d
     const long long LQ = L * p.Qp;
     const float2* G = reinterpret_cast<const float2*>(w + p.off_G);
     float* Aslab[2] = {reinterpret_cast<float*>(w + p.off_A), reinterpret_cast<float*>(w + p.off_A + p.a_slab)};
-    SFA_CUDA_CHECK(cudaEventRecord(ss->fork, st));               // G is ready / earlier work ordered
+    float2* dF = reinterpret_cast<float2*>(w + p.off_dF);
+    d_to_float_kernel<<<grid1d(F * Cd), 256, 0, st>>>(dd, F * Cd, dF);
+    SFA_LAUNCH_CHECK();
+    SFA_CUDA_CHECK(cudaEventRecord(ss->fork, st));               // G, dF are ready / earlier work ordered
     SFA_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
     int slot = 0;
     long long it = 0;
     for (long long f0 = 0; f0 < F; f0 += p.fc, ++it, slot ^= 1) {
         const long long nf = (F - f0 < p.fc) ? (F - f0) : p.fc;
         if (it >= 2) SFA_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->done[slot], 0));
-        for (long long g0 = 0; g0 < nf; g0 += 64) {
-            const int ng = (int)((nf - g0 < 64) ? nf - g0 : 64);
-            int rc = launch_steer_build(G, dd + f0 * Cd, Cd, g0, ng, LQ, is_hybrid(s), Aslab[slot] + g0 * 4 * LQ, ss->stream);
+        {
+            int rc = launch_steer_build(G, dF + f0 * Cd, Cd, 0, (int)nf, LQ, is_hybrid(s), Aslab[slot], ss->stream);
             if (rc != SFA_OK) return rc;
         }
         SFA_CUDA_CHECK(cudaEventRecord(ss->built[slot], ss->stream));

@@ -36,9 +36,11 @@ class _DeferredChecks:
 
     def __init__(self):
         self.pending = []
+        self.pool = []
 
     def add(self, status):
-        host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+        # pinned buffers are recycled: cudaHostAlloc per call would cost more than the kernels
+        host = self.pool.pop() if self.pool else torch.empty(4, dtype=torch.int32, pin_memory=True)
         host.copy_(status, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -51,7 +53,9 @@ class _DeferredChecks:
                 keep.append((ev, host))
                 continue
             ev.synchronize()
-            _raise_for_status(host.tolist())
+            st = host.tolist()
+            self.pool.append(host)
+            _raise_for_status(st)
         self.pending = keep
 
 
@@ -63,7 +67,9 @@ def check_deferred():
     pending, _deferred.pending = _deferred.pending, []
     for ev, host in pending:
         ev.synchronize()
-        _raise_for_status(host.tolist())
+        st = host.tolist()
+        _deferred.pool.append(host)
+        _raise_for_status(st)
 
 
 def _raise_for_status(st):
