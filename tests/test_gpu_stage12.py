@@ -158,3 +158,20 @@ def test_mode_matrices(mic, golden):
     assert_close(cpu(R.diagonal_mode_mat(v[:, :3])), g["diag_out"], rtol=0, floor=0)
     assert_close(cpu(R.diagonal_mode_mat(v[0, :3])), g["diag_out_1"], rtol=0, floor=0)
     assert_close(cpu(R.circ_diagonal_mode_mat(v[:, :3])), g["cdiag_out"], rtol=0, floor=0)
+
+
+def test_empty_and_degenerate_inputs(mic):
+    """Edge cases: no points / no bins / order 0 -- same shapes as the reference (oracle)."""
+    A, R = mic.modal.angular, mic.modal.radial
+    Y = A.sht_matrix(3, [], [])
+    assert tuple(Y.shape) == O.sht_matrix(3, [], []).shape == (0, 16)
+    assert tuple(A.cht_matrix(2, []).shape) == O.cht_matrix(2, []).shape == (0, 5)
+    assert tuple(R.weights(4, [], "rigid").shape) == O.weights(4, [], "rigid").shape
+    assert_close(cpu(A.sht_matrix(0, [0.1, 0.2, 0.3], [1.0, 1.1, 1.2])), O.sht_matrix(0, [0.1, 0.2, 0.3], [1.0, 1.1, 1.2]), **TOL)
+    assert_close(cpu(R.weights(0, [0.0, 0.5, 7.0], "rigid")), O.weights(0, [0.0, 0.5, 7.0], "rigid"), **TOL)
+    assert_close(cpu(R.circular_pw(0, np.array([0.0, 0.5, 7.0]), 1.0, "card")), O.circular_pw(0, np.array([0.0, 0.5, 7.0]), 1.0, "card"), **TOL)
+    # one very large order (table in shared memory) and one very large argument
+    az, co, w = O.fibonacci_grid(50)
+    assert_close(cpu(A.sht_matrix(60, az, co)), O.sht_matrix(60, az, co), rtol=1e-10, floor=4e-15)
+    kr = np.array([1e-8, 1e-3, 250.0, 900.0])
+    assert_close(cpu(R.weights(6, kr, "card")), O.weights(6, kr, "card"), rtol=1e-10, floor=1e-14)

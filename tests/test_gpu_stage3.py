@@ -270,3 +270,25 @@ def test_pwd_many_chunks(mic, monkeypatch, precision):
     dn_ref, _ = O.regularize(1 / O.spherical_pw(N, k, 0.042, "rigid"), 100, "softclip")
     ref = O.pwd_factored(Yq_ref, O.repeat_n_m(dn_ref), Yp_ref, cpu(X).astype(np.complex128))
     assert bin_err(cpu(q_many), ref) < (TOL128 if precision == "c128" else TOL64)
+
+
+def test_pwd_degenerate(mic):
+    import torch
+    A, R, S = mic.modal.angular, mic.modal.radial, mic.modal.steering
+    az, co, w = O.fibonacci_grid(9)
+    Y_p, Y_q = A.sht_matrix(2, az, co, w), A.sht_matrix(2, az[:4], co[:4])
+    dn = torch.ones((0, 3), dtype=torch.complex128, device="cuda")
+    q = S.pwd(Y_q, dn, Y_p, torch.zeros((0, 9, 5), dtype=torch.complex64, device="cuda"))
+    assert tuple(q.shape) == (0, 4, 5)
+    with pytest.raises(ValueError):
+        S.pwd(Y_q, torch.ones((2, 4), dtype=torch.complex128, device="cuda"), Y_p,
+              torch.zeros((2, 9, 5), dtype=torch.complex64, device="cuda"))          # 4 columns: neither M nor N+1
+    with pytest.raises(ValueError):
+        S.pwd(Y_q, torch.ones((2, 3), dtype=torch.complex128, device="cuda"), Y_p,
+              torch.zeros((2, 8, 5), dtype=torch.complex64, device="cuda"))          # Q mismatch
+    # 2-D p (T axis added as in np.matmul(A, p[:, :, None])) and a single bin
+    dn1 = torch.tensor([[1.0, 2.0 + 1j, -0.5j]], dtype=torch.complex128, device="cuda")
+    p = torch.randn((1, 9), dtype=torch.complex128, device="cuda")
+    q = S.pwd(Y_q, dn1, Y_p, p)
+    ref = O.pwd_factored(cpu(Y_q), O.repeat_n_m(cpu(dn1))[None, :], cpu(Y_p), cpu(p))
+    assert tuple(q.shape) == (1, 4, 1) and bin_err(cpu(q), ref) < TOL128
