@@ -136,6 +136,23 @@ SFA_HD void sph_jn_array(int nmax, double x, dvec j) {
     double fp = 0.0, f = 1.0e-30;
     double cf = (2 * n + 1) * ix;
     const double dcf = 2.0 * ix;
+    // four steps per overflow check: one step grows the pair by at most (2n+1)/x, so from 1e150
+    // four steps stay finite as long as x is not absurdly small (then: one check per step)
+    if (x > 1e-30) {
+        for (; n > nmax + 4; n -= 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double t = cf * f - fp;
+                cf -= dcf;
+                fp = f;
+                f = t;
+            }
+            if (fabs(f) > kRescaleHi) {
+                f *= kRescaleLo;
+                fp *= kRescaleLo;
+            }
+        }
+    }
     for (; n > nmax + 1; --n) {
         const double t = cf * f - fp;
         cf -= dcf;
@@ -264,39 +281,31 @@ SFA_HD double tikh_alpha(double a0) {
 
 enum RegMethod { REG_NONE = 0, REG_DISCARD = 1, REG_HARDCLIP = 2, REG_SOFTCLIP = 3, REG_TIKH = 4, REG_WNG = 5 };
 
-// d = 1/b and |d|^2 in one go.  In the range where b.re^2 + b.im^2 can neither overflow nor lose
-// bits to underflow this is conj(b)/|b|^2 (one division); otherwise NumPy's Smith division and
-// hypot, so that the Inf/NaN/underflow behaviour of the reference is reproduced exactly.
-SFA_HD void reciprocal_mag2(c128 b, c128* d, double* dmag2, bool* fast) {
-    const double m = fmax(fabs(b.re), fabs(b.im));
-    if (m > 1e-140 && m < 1e140) {
-        const double inv = 1.0 / (b.re * b.re + b.im * b.im);
-        *d = mk(b.re * inv, -b.im * inv);
-        *dmag2 = inv;
-        *fast = true;
-    } else {
-        *d = cdiv(mk(1.0, 0.0), b);
-        *dmag2 = 0.0;
-        *fast = false;
-    }
-}
-
 SFA_HD void regularize_one(c128 dn, double a0, int method, double alpha, c128* dn_out, double* hn_out);
 
-// regularize(1/b) with the fast reciprocal when it is safe
+// regularize(1/b) in one step.  In the range where |b|^2 = b.re^2 + b.im^2 can neither overflow nor
+// lose bits to underflow the closed forms below need ONE division per value:
+//   none : d = conj(b)/|b|^2,              h = 1
+//   Tikh : d h = conj(b)/(|b|^2 + alpha^2), h = |b|^2/(|b|^2 + alpha^2)     (= 1/(1 + alpha^2 |1/b|^2))
+//   wng  : d h = conj(b),                   h = |b|^2                         (= 1/|1/b|^2)
+// (identical to the reference up to rounding).  Everything else -- the clipping methods, huge or
+// tiny |b|, Inf/NaN -- takes NumPy's Smith division + hypot so that the reference's special-value
+// behaviour is reproduced exactly.
 SFA_HD void regularize_inverse(c128 b, double a0, int method, double alpha, c128* dn_out, double* hn_out) {
-    c128 d;
-    double m2;
-    bool fast;
-    reciprocal_mag2(b, &d, &m2, &fast);
-    if (fast && (method == REG_TIKH || method == REG_WNG || method == REG_NONE)) {
-        const double h = (method == REG_TIKH) ? 1.0 / (1.0 + (alpha * alpha) * m2)
-                         : (method == REG_WNG ? 1.0 / m2 : 1.0);
-        *hn_out = h;
-        *dn_out = cmul(d, mk(h, 0.0));
+    const double m = fmax(fabs(b.re), fabs(b.im));
+    if (m > 1e-140 && m < 1e140 && (method == REG_TIKH || method == REG_WNG || method == REG_NONE)) {
+        const double m2 = b.re * b.re + b.im * b.im;
+        if (method == REG_WNG) {
+            *hn_out = m2;
+            *dn_out = mk(b.re, -b.im);
+            return;
+        }
+        const double inv = 1.0 / (method == REG_TIKH ? m2 + alpha * alpha : m2);
+        *hn_out = (method == REG_TIKH) ? m2 * inv : 1.0;
+        *dn_out = mk(b.re * inv, -b.im * inv);
         return;
     }
-    regularize_one(d, a0, method, alpha, dn_out, hn_out);
+    regularize_one(cdiv(mk(1.0, 0.0), b), a0, method, alpha, dn_out, hn_out);
 }
 
 SFA_HD void regularize_one(c128 dn, double a0, int method, double alpha, c128* dn_out, double* hn_out) {

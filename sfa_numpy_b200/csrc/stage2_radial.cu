@@ -30,14 +30,16 @@ struct TileOut {
 __device__ __forceinline__ bool is_zero_entry(double2 v) { return cabs_less(mk(v.x, v.y), kZeroThreshold); }
 
 // status[0] zero count, [1] unrepairable column, [2] worklist overflow, [3] worklist length
+// FAMILY / SETUP / SCALE are compile-time so the per-order loop carries no mode branches.
+template <int FAMILY, int SETUP, int SCALE>
 __global__ void __launch_bounds__(kRadialThreads)
-radial_filter_kernel(int family, int N, long long F, const double* __restrict__ k, double r, double rs,
-                     int setup, int scale, int want_zero_list, int method, double a0, double alpha,
+radial_filter_kernel(int N, long long F, const double* __restrict__ k, double r, double rs,
+                     int want_zero_list, int method, double a0, double alpha,
                      double2* __restrict__ bn, double2* __restrict__ dn, double* __restrict__ hn_real,
                      double2* __restrict__ hn_cplx, int* __restrict__ status,
                      long long* __restrict__ worklist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int C = family ? 2 * N + 1 : N + 1;
+    const int C = FAMILY ? 2 * N + 1 : N + 1;
     const int Cp = C | 1;                                   // odd row pitch: conflict-free 16 B rows
     const int T = blockDim.x;
     double2* tile = reinterpret_cast<double2*>(smem_raw);   // [T][Cp]
@@ -51,15 +53,21 @@ radial_filter_kernel(int family, int N, long long F, const double* __restrict__ 
             dvec jx{scratch + tid, T};
             dvec js{scratch + (size_t)(N + 3) * T + tid, T};
             TileOut out{tile + (size_t)tid * Cp};
-            if (family == 0) sph_radial_row(N, k[f], r, rs, setup, scale, jx, js, out);
-            else circ_radial_row(N, k[f], r, rs, setup, scale, jx, js, out);
+            if (FAMILY == 0) sph_radial_row(N, k[f], r, rs, SETUP, SCALE, jx, js, out);
+            else circ_radial_row(N, k[f], r, rs, SETUP, SCALE, jx, js, out);
         }
         __syncthreads();
         const int rows = (int)((F - f0 < T) ? (F - f0) : T);
         const int total = rows * C;
         int local_zero = 0;
-        for (int e = tid; e < total; e += T) {
-            const int rr = e / C, cc = e - rr * C;
+        // (row, col) of element e = tid, tid + T, ... tracked incrementally (no division per element)
+        int rr = tid / C, cc = tid - rr * C;
+        const int drr = T / C, dcc = T - drr * C;
+        for (int e = tid; e < total; e += T, rr += drr, cc += dcc) {
+            if (cc >= C) {
+                cc -= C;
+                ++rr;
+            }
             const double2 b = tile[(size_t)rr * Cp + cc];
             const long long g = f0 * C + e;
             bn[g] = b;
@@ -262,7 +270,6 @@ extern "C" int sfa_radial_filter(int kind, int N, int64_t F, const double* k, do
     const int T = kRadialThreads;
     const size_t smem = (size_t)T * Cp * sizeof(double2) + (size_t)(scale == 2 ? 2 : 1) * (N + 3) * T * sizeof(double);
     if (smem > 220 * 1024) return SFA_ERR_UNSUPPORTED;
-    SFA_CUDA_CHECK(cudaFuncSetAttribute(radial_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const double alpha = (method == SFA_REG_TIKH) ? tikh_alpha(a0) : 0.0;
     double* hr;
     double2* hc;
@@ -271,9 +278,24 @@ extern "C" int sfa_radial_filter(int kind, int N, int64_t F, const double* k, do
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     long long* wl = reinterpret_cast<long long*>(work);
-    radial_filter_kernel<<<(unsigned)blocks, T, smem, st>>>(
-        family, N, F, k, r, rs, setup, scale, replace_zeros ? 1 : 0, method, a0, alpha,
-        reinterpret_cast<double2*>(bn), reinterpret_cast<double2*>(dn), hr, hc, status, wl);
+    int rc = SFA_ERR_INVALID;
+#define SFA_RADIAL_CASE(FAM, SET, SCL)                                                                         \
+    if (family == FAM && setup == SET && scale == SCL) {                                                       \
+        auto kern = radial_filter_kernel<FAM, SET, SCL>;                                                       \
+        SFA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        kern<<<(unsigned)blocks, T, smem, st>>>(N, F, k, r, rs, replace_zeros ? 1 : 0, method, a0, alpha,      \
+                                                 reinterpret_cast<double2*>(bn), reinterpret_cast<double2*>(dn), \
+                                                 hr, hc, status, wl);                                          \
+        rc = SFA_OK;                                                                                           \
+    }
+#define SFA_RADIAL_SCALES(FAM, SET) SFA_RADIAL_CASE(FAM, SET, 0) SFA_RADIAL_CASE(FAM, SET, 1) SFA_RADIAL_CASE(FAM, SET, 2)
+#define SFA_RADIAL_SETUPS(FAM) SFA_RADIAL_SCALES(FAM, 0) SFA_RADIAL_SCALES(FAM, 1) SFA_RADIAL_SCALES(FAM, 2)
+    SFA_RADIAL_SETUPS(0)
+    SFA_RADIAL_SETUPS(1)
+#undef SFA_RADIAL_SETUPS
+#undef SFA_RADIAL_SCALES
+#undef SFA_RADIAL_CASE
+    if (rc != SFA_OK) return rc;
     SFA_LAUNCH_CHECK();
     if (replace_zeros) {
         // Both kernels return at once when the zero list is empty (the normal case).

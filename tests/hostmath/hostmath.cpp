@@ -34,6 +34,11 @@ void hm_regularize(long n, const c128* dn, double a0, int method, c128* dn_out, 
     for (long i = 0; i < n; ++i) regularize_one(dn[i], a0, method, alpha, dn_out + i, hn + i);
 }
 
+void hm_regularize_inverse(long n, const c128* bn, double a0, int method, c128* dn_out, double* hn) {
+    const double alpha = (method == REG_TIKH) ? tikh_alpha(a0) : 0.0;
+    for (long i = 0; i < n; ++i) regularize_inverse(bn[i], a0, method, alpha, dn_out + i, hn + i);
+}
+
 void hm_sht(int N, long Q, const double* azi, const double* colat, int colat_scalar, const double* w, c128* Y) {
     const long M = (long)(N + 1) * (N + 1);
     for (long q = 0; q < Q; ++q)

@@ -23,6 +23,7 @@ def hm():
     lib.hm_circ_radial.argtypes = [ci, cl, vp, cd, cd, ci, ci, vp]
     lib.hm_regularize.argtypes = [cl, vp, cd, ci, vp, vp]
     lib.hm_sht.argtypes = [ci, cl, vp, vp, ci, vp, vp]
+    lib.hm_regularize_inverse.argtypes = [cl, vp, cd, ci, vp, vp]
     return lib
 
 
@@ -87,3 +88,18 @@ def test_regularize(hm, golden, mi, method):
         pre = "reg" if key == "reg_dn" else "regbig"
         assert_close(d.reshape(g[key].shape), g[pre + "_d_" + method], **TOL, name="d")
         assert_close(h.reshape(g[key].shape), np.real(g[pre + "_h_" + method]), **TOL, name="h")
+
+
+@pytest.mark.parametrize("mi,method", list(enumerate(O.METHODS)))
+def test_regularize_inverse_fused(hm, mi, method):
+    """The fused d = regularize(1/b) (one division on the fast path) against the reference sequence,
+    including |b| far outside the fast range, zeros, Inf and NaN."""
+    rng = np.random.default_rng(7)
+    b = (rng.standard_normal(400) + 1j * rng.standard_normal(400)) * 10.0 ** rng.uniform(-30, 30, 400)
+    b = np.concatenate([b, [1e-200 + 1e-210j, 1e200j, 3e-160, 0j, np.inf, complex(np.nan, 1.0), 1e-310 + 0j]])
+    with np.errstate(all="ignore"):
+        ref_d, ref_h = O.regularize(1 / b, 100.0, method)
+    d, h = np.empty_like(b), np.empty(b.shape)
+    hm.hm_regularize_inverse(b.size, P(np.ascontiguousarray(b)), 100.0, mi, P(d), P(h))
+    assert_close(h, np.real(ref_h), rtol=1e-12, floor=0.0, name="h")
+    assert_close(d, ref_d, rtol=1e-12, floor=0.0, name="d")
