@@ -1,0 +1,83 @@
+"""Stage 3 at the FULL sizes of BASELINE.json's configs 1, 2, 4 and 5 (config 3, the headline, is
+covered by test_gpu_stage3.py::test_pwd_linearity_and_plan and bench.py): the result is checked on
+a few bins against the oracle (which only finishes in seconds for a few bins at these sizes) and
+through a size-independent property (linearity in X)."""
+import numpy as np
+import pytest
+
+from oracle import sfa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+def bin_err(q, ref):
+    q = q.reshape(q.shape[0], -1)
+    ref = ref.reshape(ref.shape[0], -1)
+    return float(np.max(np.max(np.abs(q - ref), axis=1) / np.max(np.abs(ref), axis=1)))
+
+
+CONFIGS = {
+    # name: (kind, N, Q grid, F, L, T, r, setup, a0, method)
+    "cfg1": ("sph", 4, "equal_angle", 512, 360, 256, 0.042, "rigid", 100.0, "softclip"),
+    "cfg2": ("circ", 16, 32, 1024, 360, 256, 0.1, "open", 3000.0, "softclip"),
+    "cfg4": ("sph", 16, "gauss", 1024, 2562, 64, 0.1, "card", 100.0, "Tikh"),
+    "cfg5": ("sph", 32, 1089, 4096, 16384, 32, 0.2, "rigid", 100.0, "Tikh"),
+}
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_full_size_config(name):
+    import torch
+    import sfa_numpy_b200 as micarray
+    A, R, S = micarray.modal.angular, micarray.modal.radial, micarray.modal.steering
+    kind, N, grid, F, L, T, r, setup, a0, method = CONFIGS[name]
+    if kind == "sph":
+        if grid == "equal_angle":
+            az, co, w = O.grid_equal_angle(N)
+        elif grid == "gauss":
+            az, co, w = O.grid_gauss(N)
+        else:
+            az, co, w = O.fibonacci_grid(grid)
+        if name == "cfg1":
+            azl, col = np.linspace(0, 2 * np.pi, L, endpoint=False), np.full(L, np.pi / 2)
+        else:
+            azl, col, _ = O.fibonacci_grid(L)
+        Y_p, Y_q = A.sht_matrix(N, az, co, w), A.sht_matrix(N, azl, col)
+        k = O.wavenumbers(F) if name != "cfg4" else np.geomspace(0.01, 50, F) / r
+        _, dn, _ = R.radial_filters(N, k, r, setup, a0, method)
+        Yp_ref, Yq_ref = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
+        with np.errstate(all="ignore"):
+            dn_ref, _ = O.regularize(1 / O.spherical_pw(N, k, r, setup), a0, method)
+        dcols = O.repeat_n_m(dn_ref)
+    else:
+        pol = np.linspace(0, 2 * np.pi, grid, endpoint=False)
+        poll = np.linspace(0, 2 * np.pi, L, endpoint=False)
+        w = np.full(grid, 1.0 / grid)
+        Y_p, Y_q = A.cht_matrix(N, pol, w), A.cht_matrix(N, poll)
+        k = O.wavenumbers(F)
+        _, dn, _ = R.radial_filters(N, k, r, setup, a0, method, kind="circular_pw")
+        Yp_ref, Yq_ref = O.cht_matrix(N, pol, w), O.cht_matrix(N, poll)
+        with np.errstate(all="ignore"):
+            dn_ref, _ = O.regularize(1 / O.circular_pw(N, k, r, setup), a0, method)
+        dcols = dn_ref
+    Q = Y_p.shape[0]
+    assert np.max(np.abs(cpu(dn) - dn_ref) / (np.abs(dn_ref) + 1e-300)) < 1e-9
+    g = torch.Generator(device="cuda").manual_seed(11)
+    X1 = torch.randn((F, Q, T), dtype=torch.complex64, device="cuda", generator=g)
+    X2 = torch.randn((F, Q, T), dtype=torch.complex64, device="cuda", generator=g)
+    plan = S.PwdPlan(Y_q, dn, Y_p, T, precision="c64_fast")
+    q1 = plan(X1)
+    assert tuple(q1.shape) == (F, L, T) and bool(torch.isfinite(torch.view_as_real(q1)).all())
+    # spot bins against the oracle (factored form; dense reference chain is infeasible here)
+    sel = [1, F // 2, F - 1]
+    ref = O.pwd_factored(Yq_ref, dcols[sel], Yp_ref, cpu(X1[sel]).astype(np.complex128))
+    assert bin_err(cpu(q1[sel]), ref) < 1e-5
+    # linearity over the whole output
+    q2 = plan(X2)
+    q12 = plan(X1 + 2 * X2)
+    num = float((q12 - (q1 + 2 * q2)).abs().max())
+    assert num / float(q12.abs().max()) < 5e-6
