@@ -200,9 +200,7 @@ def main():
     import torch
     import torch.distributed as dist
     from oracle import sfa_oracle as O            # synthetic-input generator + cpu_baseline only
-    import __graft_entry__ as G
-    G.build()
-    import sfa_numpy_b200 as micarray
+    import sfa_numpy_b200 as micarray          # loads the prebuilt libsfa_b200.so; raises if it is missing
     from sfa_numpy_b200 import _lib
     import ctypes
 

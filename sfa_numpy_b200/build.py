@@ -20,13 +20,30 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+STAMP = os.path.join(HERE, "lib", "build.stamp")
+
+
+def source_hash():
+    """Content hash of everything the library is built from (robust to mtime changes when the tree is
+    copied to another machine)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
+        sorted(glob.glob(os.path.join(HERE, "..", "include", "*.h")))
+    for p in deps:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(b"debug" if os.environ.get("SFA_BUILD_DEBUG_HOOKS") else b"")
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + \
-        glob.glob(os.path.join(HERE, "..", "include", "*.h"))
-    return any(os.path.getmtime(p) > t for p in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -35,13 +52,17 @@ def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     extra = ["-DSFA_DEBUG_HOOKS"] if os.environ.get("SFA_BUILD_DEBUG_HOOKS") else []
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libsfa_b200.so")
+    os.replace(tmp, LIB)
     if verbose:
         sys.stderr.write(res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(source_hash())
     return LIB
 
 

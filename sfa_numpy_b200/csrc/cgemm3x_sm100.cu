@@ -61,7 +61,7 @@ constexpr int kOperandCol0 = 2 * kAccCols;               // 256
 constexpr int kStoreRows = 16;                           // rows (n) per TMA store box
 constexpr int kStoreBytes = kStoreRows * kTileM * 8;     // 16 KB staging buffer per epilogue half
 
-enum OutMode { OUT_C64 = 0, OUT_C64_ACCUM = 2 };
+enum OutMode { OUT_C64 = 0, OUT_C64_FIRST_OF_MANY = 1 /* plain store, first split-K pass */, OUT_C64_ACCUM = 2 };
 
 struct GemmParams {
     long long B, Nn, Mm;
@@ -78,6 +78,7 @@ struct GemmParams {
     long long tasks;        // B * m_tiles
     int n_tiles;            // ceil(Nn / 64)
     int debug_no_tma;
+    int fold;               // P shared and Mm <= 64: m-tiles run over the folded (batch, m) axis
     int issuers;            // MMA issuer warps per CTA (1 or 2)
     int csize;              // CTAs per cluster sharing the P stream by TMA multicast (1 or 2)
     int m_groups;           // ceil(m_tiles / csize)
@@ -293,7 +294,7 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
     const uint32_t crank = (csize > 1) ? cluster_ctarank() : 0u;
     const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
     const long long cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
-    const long long n_groups = prm.B * prm.m_groups;
+    const long long n_groups = prm.fold ? prm.m_groups : prm.B * prm.m_groups;
     const int ksteps = (prm.K + 7) >> 3;               // MMA k-steps of 8
     const int kboxes = (prm.K + kBoxK - 1) / kBoxK;    // TMA boxes along k (1 or 2)
 
@@ -455,10 +456,18 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         uint32_t a_phase = 0;
         for (long long grp = cluster_id; grp < n_groups; grp += n_clusters) {
-            const long long b = grp / prm.m_groups;
-            const int mt = (int)(grp - b * prm.m_groups) * csize + (int)crank;
-            const long long m = (long long)mt * kTileM + quarter * 32 + lane;
-            const bool m_ok = m < prm.Mm;
+            // (b, m) of this lane's row; in folded mode consecutive rows run through several batches
+            long long b = grp / prm.m_groups;
+            int mt = (int)(grp - b * prm.m_groups) * csize + (int)crank;
+            long long m = (long long)mt * kTileM + quarter * 32 + lane;
+            bool m_ok = m < prm.Mm;
+            if (prm.fold) {
+                mt = (int)grp * csize + (int)crank;
+                const long long mg = (long long)mt * kTileM + quarter * 32 + lane;
+                m_ok = mg < prm.B * prm.Mm;
+                b = m_ok ? mg / prm.Mm : 0;
+                m = mg - b * prm.Mm;
+            }
             const float2* src = prm.R + b * prm.strideR + (m_ok ? m : 0);
             float2 v[32];
 #pragma unroll
@@ -515,10 +524,17 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long long grp = cluster_id; grp < n_groups; grp += n_clusters) {
-            const long long b = grp / prm.m_groups;
-            const int mt = (int)(grp - b * prm.m_groups) * csize + (int)crank;
-            const long long m = (long long)mt * kTileM + quarter * 32 + lane;
-            const bool m_ok = m < prm.Mm;
+            long long b = grp / prm.m_groups;
+            int mt = (int)(grp - b * prm.m_groups) * csize + (int)crank;
+            long long m = (long long)mt * kTileM + quarter * 32 + lane;
+            bool m_ok = m < prm.Mm;
+            if (prm.fold) {
+                mt = (int)grp * csize + (int)crank;
+                const long long mg = (long long)mt * kTileM + quarter * 32 + lane;
+                m_ok = mg < prm.B * prm.Mm;
+                b = m_ok ? mg / prm.Mm : 0;
+                m = mg - b * prm.Mm;
+            }
             const bool all_ok = __all_sync(0xffffffffu, m_ok);   // false only in a ragged last m-tile
             float2* const out_bm = reinterpret_cast<float2*>(prm.out) + b * prm.strideO + (m_ok ? m : 0);
             const float2* const scale_b = prm.rowscale ? prm.rowscale + b * prm.strideS : nullptr;
@@ -692,7 +708,11 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
         return SFA_ERR_CUDA;
     }
     // Output tensor map for the TMA-store epilogue: fp32 view [B][Nn][2*ldo], box = 16 rows x 128 complex.
-    const int tma_store = ((ldo & 1) == 0 && (strideO & 1) == 0 && (((uintptr_t)out) & 15) == 0 &&
+    // Small m extents with a shared P (factored form at small T): fold batches into the m-tiles.
+    // Only for single-pass products: the split-K accumulate passes rely on the TMA reduce-add store,
+    // which needs whole tiles inside one batch (measured: folding + register read-modify-write is slower).
+    const int fold = (p_shared && Mm <= 64 && B > 1 && out_mode == OUT_C64 && !getenv("SFA_NO_FOLD")) ? 1 : 0;
+    const int tma_store = (!fold && (ldo & 1) == 0 && (strideO & 1) == 0 && (((uintptr_t)out) & 15) == 0 &&
                            !getenv("SFA_NO_TMA_STORE")) ? 1 : 0;
     CUtensorMap omap = map;
     if (tma_store) {
@@ -729,7 +749,8 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     prm.out_mode = out_mode;
     prm.debug_no_tma = 0;
 #endif
-    prm.m_tiles = (int)ceil_div(Mm, kTileM);
+    prm.fold = fold;
+    prm.m_tiles = (int)ceil_div(fold ? B * Mm : Mm, kTileM);
     prm.tasks = B * prm.m_tiles;
     prm.n_tiles = (int)ceil_div(Nn, kTileN);
     const size_t smem = (size_t)kStagesB * kStageBytes + 2 * kStoreBytes + sizeof(Barriers) + 1024;
@@ -743,7 +764,7 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     const int csize = (prm.m_tiles >= 2 && !getenv("SFA_NO_CLUSTER")) ? 2 : 1;
     prm.csize = csize;
     prm.m_groups = (prm.m_tiles + csize - 1) / csize;
-    const long long n_groups = B * prm.m_groups;
+    const long long n_groups = (fold ? 1 : B) * prm.m_groups;
     const long long max_clusters = sm_count() / csize;
     const long long grid = (n_groups < max_clusters ? n_groups : max_clusters) * csize;
     cudaLaunchConfig_t cfg = {};

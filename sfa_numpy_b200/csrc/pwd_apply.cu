@@ -24,7 +24,7 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
                    long long strideO, int out_mode, const float2* rowscale, long long strideS, int hybrid,
                    cudaStream_t st);
 
-constexpr int kOutC64 = 0, kOutAccum = 2;
+constexpr int kOutC64 = 0, kOutFirstOfMany = 1, kOutAccum = 2;
 
 __device__ __forceinline__ uint32_t tf32_rna(float x) {
     uint32_t r;
@@ -386,9 +386,10 @@ static int cgemm_splitk(long long B, long long Nn, long long Mm, long long K, co
                         long long strideO, const float2* rowscale, long long strideS, int hybrid, cudaStream_t st) {
     for (long long k0 = 0; k0 < K; k0 += 64) {
         const int kc = (int)((K - k0 < 64) ? (K - k0) : 64);
+        // the first pass of a split-K product is marked too, so that every pass uses the same (unfolded) tiling
+        const int mode = (k0 == 0) ? (K > 64 ? kOutFirstOfMany : kOutC64) : kOutAccum;
         int rc = launch_cgemm3x(B, Nn, Mm, kc, Pp + k0, Kp, p_shared, R + k0 * ldR, ldR, strideR,
-                                reinterpret_cast<float*>(out), ldo, strideO, k0 == 0 ? kOutC64 : kOutAccum,
-                                rowscale, strideS, hybrid, st);
+                                reinterpret_cast<float*>(out), ldo, strideO, mode, rowscale, strideS, hybrid, st);
         if (rc != SFA_OK) return rc;
     }
     return SFA_OK;
