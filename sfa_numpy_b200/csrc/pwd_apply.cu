@@ -131,32 +131,48 @@ __global__ void __launch_bounds__(128)
 steer_build_split_kernel(const float2* __restrict__ G, const float2* __restrict__ d, int Cd, int ngroups,
                          long long f0, int nf, long long LQ, int hybrid, float* __restrict__ A) {
     // No shared memory and 128 threads: one of these CTAs fits on an SM beside the (persistent)
-    // GEMM CTA, so this kernel really runs under the GEMM of the previous chunk.
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < LQ;
-         e += (long long)gridDim.x * blockDim.x) {
-        float2 g[NG];
+    // GEMM CTA.  Each thread owns TWO adjacent steering entries (LQ is a multiple of 4), so every
+    // store instruction of a warp writes 256 contiguous bytes of one plane.
+    const long long pairs = LQ >> 1;
+    for (long long e2 = (long long)blockIdx.x * blockDim.x + threadIdx.x; e2 < pairs;
+         e2 += (long long)gridDim.x * blockDim.x) {
+        const long long e = e2 * 2;
+        float4 g[NG];                                   // (re0, im0, re1, im1) of the two entries
 #pragma unroll
-        for (int c = 0; c < NG; ++c) g[c] = (c < ngroups) ? __ldg(G + (long long)c * LQ + e) : make_float2(0.f, 0.f);
-        float* o = A + e;
-        for (int f = 0; f < nf; ++f) {
+        for (int c = 0; c < NG; ++c)
+            g[c] = (c < ngroups) ? __ldg(reinterpret_cast<const float4*>(G + (long long)c * LQ + e))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        // blockIdx.y slices the bins of the chunk (more CTAs in flight: the kernel is store-latency bound)
+        const int fs = (nf + (int)gridDim.y - 1) / (int)gridDim.y;
+        const int fa = (int)blockIdx.y * fs, fb = (fa + fs < nf) ? fa + fs : nf;
+        float* o = A + e + (long long)fa * 4 * LQ;
+        for (int f = fa; f < fb; ++f) {
             const float2* df = d + (f0 + f) * Cd;           // warp-uniform address: broadcast through L1
-            float ar = 0.f, ai = 0.f;
+            float ar0 = 0.f, ai0 = 0.f, ar1 = 0.f, ai1 = 0.f;
 #pragma unroll
             for (int c = 0; c < NG; ++c) {
                 if (c < ngroups) {
                     const float2 dd = __ldg(df + c);
-                    const float dx = dd.x, dy = dd.y;
-                    ar = fmaf(dx, g[c].x, ar);
-                    ar = fmaf(-dy, g[c].y, ar);
-                    ai = fmaf(dx, g[c].y, ai);
-                    ai = fmaf(dy, g[c].x, ai);
+                    ar0 = fmaf(dd.x, g[c].x, ar0);
+                    ar0 = fmaf(-dd.y, g[c].y, ar0);
+                    ai0 = fmaf(dd.x, g[c].y, ai0);
+                    ai0 = fmaf(dd.y, g[c].x, ai0);
+                    ar1 = fmaf(dd.x, g[c].z, ar1);
+                    ar1 = fmaf(-dd.y, g[c].w, ar1);
+                    ai1 = fmaf(dd.x, g[c].w, ai1);
+                    ai1 = fmaf(dd.y, g[c].z, ai1);
                 }
             }
-            const float hr = __uint_as_float(tf32_rna(ar)), hi = __uint_as_float(tf32_rna(ai));
-            __stcs(o, hr);
-            __stcs(o + LQ, hi);
-            __stcs(o + 2 * LQ, hybrid ? pack_bf16_lo_hi(hr, ar - hr) : ar - hr);
-            __stcs(o + 3 * LQ, hybrid ? pack_bf16_lo_hi(hi, ai - hi) : ai - hi);
+            const float hr0 = __uint_as_float(tf32_rna(ar0)), hi0 = __uint_as_float(tf32_rna(ai0));
+            const float hr1 = __uint_as_float(tf32_rna(ar1)), hi1 = __uint_as_float(tf32_rna(ai1));
+            __stcs(reinterpret_cast<float2*>(o), make_float2(hr0, hr1));
+            __stcs(reinterpret_cast<float2*>(o + LQ), make_float2(hi0, hi1));
+            __stcs(reinterpret_cast<float2*>(o + 2 * LQ),
+                   hybrid ? make_float2(pack_bf16_lo_hi(hr0, ar0 - hr0), pack_bf16_lo_hi(hr1, ar1 - hr1))
+                          : make_float2(ar0 - hr0, ar1 - hr1));
+            __stcs(reinterpret_cast<float2*>(o + 3 * LQ),
+                   hybrid ? make_float2(pack_bf16_lo_hi(hi0, ai0 - hi0), pack_bf16_lo_hi(hi1, ai1 - hi1))
+                          : make_float2(ai0 - hi0, ai1 - hi1));
             o += 4 * LQ;
         }
     }
@@ -169,7 +185,7 @@ __global__ void d_to_float_kernel(const double2* __restrict__ d, long long n, fl
 
 static int launch_steer_build(const float2* G, const float2* d, int Cd, long long f0, int nf, long long LQ,
                               int hybrid, float* A, cudaStream_t st) {
-    const unsigned grid = (unsigned)ceil_div(LQ, 128);
+    const dim3 grid((unsigned)ceil_div(LQ / 2, 128), (unsigned)ceil_div(nf, 8));
     if (Cd <= 16)
         steer_build_split_kernel<16><<<grid, 128, 0, st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
     else if (Cd <= 32)
