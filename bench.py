@@ -279,11 +279,20 @@ def main():
     alg_flops = 8.0 * F * L * Q * T
     peaks, peak_src = load_peaks()
     achieved = alg_bytes / (gemm_ms_per_step * 1e-3) / 1e9
+    n_prof = max(2, min(args.steps, 5))
+    launches_per_step = cnt.value / n_prof
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (74 bins) from the committed ncu
+    # capture profiles/r1_f_cgemm3x_hybrid_cluster_tmastore.txt; bench.py itself never runs under ncu.
+    NCU_TRAFFIC_74_BINS = 1.380845e9 + 0.292279e9
     roofline = {"kernel": "cgemm3x_kernel<%s> (tcgen05 steering GEMM)" % ("hybrid" if args.precision == "c64_fast" else "3xTF32"), "bound": "hbm",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "frac": achieved / peaks["hbm_gbs"],
+                "traffic": NCU_TRAFFIC_74_BINS if args.precision == "c64_fast" else None,
+                "traffic_source": "ncu --set full, one 74-bin launch (profiles/r1_f_cgemm3x_hybrid_cluster_tmastore.txt)",
+                "alg_bytes_per_launch": alg_bytes / launches_per_step if launches_per_step else None,
+                "kernel_ms_per_launch": gemm_ms_per_step / launches_per_step if launches_per_step else None,
                 "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
-                "launches_per_step": cnt.value / max(2, min(args.steps, 5)),
+                "launches_per_step": launches_per_step,
                 "kernel_ms_per_step": gemm_ms_per_step, "kernel_share_of_step": gemm_ms_per_step / (ms / args.steps),
                 "alg_bytes_per_step": alg_bytes, "alg_tflops_achieved": alg_flops / (gemm_ms_per_step * 1e-3) / 1e12}
 
