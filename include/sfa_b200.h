@@ -125,6 +125,20 @@ int sfa_repeat_n_m(int64_t F, int N, const sfa_c128* v, sfa_c128* out, void* str
  * (radial.py:285-290, 459-464): d [F, M] -> D [F, M, M] dense, zeros off the diagonal. */
 int sfa_diagonal_stack(int64_t F, int M, const sfa_c128* d, sfa_c128* D, void* stream);
 
+/* ---- "next" rows: remaining angular / util surface ---------------------- */
+
+/* angular.Legendre_matrix (angular.py:73-103): L[n, q] = (2n+1)/(4 pi) P_n(ctheta[q]), [(N+1), Q]. */
+int sfa_legendre_matrix(int N, int64_t Q, const double* ctheta, sfa_c128* L, void* stream);
+/* util.matdiagmul (util.py:65-93): C[k, m, n] = A[m, n] * b[k, n]. */
+int sfa_matdiagmul(int64_t K, int64_t M, int64_t N, const sfa_c128* A, const sfa_c128* b, sfa_c128* C,
+                   void* stream);
+/* util.norm_of_columns (util.py:5-21): p-norm of each column of A [M, N]. */
+int sfa_norm_of_columns(int64_t M, int64_t N, const sfa_c128* A, double p, double* out, void* stream);
+/* util.coherence_of_columns (util.py:24-45): max off-diagonal |Gram| of the column-normalised A.
+ * norms: device scratch [N]; result: device double. */
+int sfa_coherence_of_columns(int64_t M, int64_t N, const sfa_c128* A, double* norms, double* result,
+                             void* stream);
+
 /* ---- stage 3: plane-wave decomposition / steering ------------------------------ */
 
 /* q_f = Y_L * diag(d_f) * Y_Q^H * X_f   for every bin f  -- the example idiom

@@ -377,3 +377,38 @@ def synth_spectra(F, Q, T, seed=0, dtype=np.complex64):
         X[f].real = (g[0] * np.float32(np.sqrt(0.5))).astype(real_t)
         X[f].imag = (g[1] * np.float32(np.sqrt(0.5))).astype(real_t)
     return X
+
+
+# --------------------------------------------------------------------------
+# "next" rows
+# --------------------------------------------------------------------------
+def Legendre_matrix(N, ctheta):
+    """angular.py:73-103: ``(2n+1)/(4 pi) * polyval(legendre(n), ctheta)``, shape (N+1, Q), complex."""
+    ctheta = np.asarray(ctheta)
+    M = 1 if ctheta.ndim == 0 else len(ctheta)
+    out = np.zeros((N + 1, M), dtype=complex)
+    for n in range(N + 1):
+        out[n, :] = (2 * n + 1) / (4 * np.pi) * np.polyval(special.legendre(n), ctheta)
+    return out
+
+
+def matdiagmul(A, b):
+    """util.py:65-93: ``C[k] = A * b[k]``."""
+    b = np.asarray(b)
+    if b.ndim == 1:
+        b = b[None, :]
+    return np.asarray(A)[None, :, :] * b[:, None, :]
+
+
+def norm_of_columns(A, p=2):
+    """util.py:5-21."""
+    return np.linalg.norm(np.asarray(A), ord=p, axis=0)
+
+
+def coherence_of_columns(A):
+    """util.py:24-45: max off-diagonal magnitude of the Gram matrix of the column-normalised A."""
+    A = np.asarray(A)
+    An = A / norm_of_columns(A)[None, :]
+    G = An.conj().T @ An
+    np.fill_diagonal(G, 0)
+    return np.max(np.abs(G))

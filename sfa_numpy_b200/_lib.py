@@ -40,6 +40,10 @@ SIGNATURES = {
     "sfa_regularize": (c_int, [c_int64, c_void_p, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "sfa_repeat_n_m": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "sfa_diagonal_stack": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "sfa_legendre_matrix": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "sfa_matdiagmul": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sfa_norm_of_columns": (c_int, [c_int64, c_int64, c_void_p, c_double, c_void_p, c_void_p]),
+    "sfa_coherence_of_columns": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfa_pwd_work_bytes": (c_size_t, [ctypes.POINTER(PwdShape)]),
     "sfa_pwd_apply": (c_int, [ctypes.POINTER(PwdShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_void_p]),

@@ -1,0 +1,146 @@
+// "Next" rows of SURVEY section 8f: the rest of the reference's angular/util surface.
+//   sfa_legendre_matrix   <- angular.Legendre_matrix        micarray/modal/angular.py:73-103
+//   sfa_matdiagmul        <- util.matdiagmul                micarray/util.py:65-93
+//   sfa_norm_of_columns   <- util.norm_of_columns           micarray/util.py:5-21
+//   sfa_coherence_of_columns <- util.coherence_of_columns   micarray/util.py:24-45
+#include "sfa_common.cuh"
+
+namespace sfa {
+
+// L[n][q] = (2n+1)/(4 pi) P_n(x_q).  The reference evaluates np.polyval(scipy.special.legendre(n), x)
+// (coefficient form, ill-conditioned for large n); here the three-term recurrence
+// (n+1) P_{n+1} = (2n+1) x P_n - n P_{n-1}, which is stable for |x| <= 1.
+__global__ void legendre_matrix_kernel(int N, long long Q, const double* __restrict__ x, double2* __restrict__ L) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q;
+         q += (long long)gridDim.x * blockDim.x) {
+        const double xq = x[q];
+        const double inv4pi = 0.07957747154594767;      // 1 / (4 pi)
+        double pm = 1.0, p = xq;
+        L[q] = make_double2(inv4pi, 0.0);
+        if (N >= 1) L[Q + q] = make_double2(3.0 * inv4pi * xq, 0.0);
+        for (int n = 1; n < N; ++n) {
+            const double pn = ((2 * n + 1) * xq * p - n * pm) / (n + 1);
+            pm = p;
+            p = pn;
+            L[(long long)(n + 1) * Q + q] = make_double2((2 * n + 3) * inv4pi * pn, 0.0);
+        }
+    }
+}
+
+// C[k][m][n] = A[m][n] * b[k][n]
+__global__ void matdiagmul_kernel(long long K, long long M, long long N, const double2* __restrict__ A,
+                                  const double2* __restrict__ b, double2* __restrict__ C) {
+    const long long total = K * M * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long k = i / (M * N), r = i - k * M * N;
+        const long long n = r % N;
+        const double2 a = A[r], v = b[k * N + n];
+        C[i] = make_double2(a.x * v.x - a.y * v.y, a.x * v.y + a.y * v.x);
+    }
+}
+
+// one warp per column: (sum_m |A[m][j]|^p)^(1/p); p = 2 uses a scaled sum of squares
+__global__ void norm_of_columns_kernel(long long M, long long N, const double2* __restrict__ A, double p,
+                                       double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long j = warp; j < N; j += nwarps) {
+        double acc = 0.0;
+        for (long long m = lane; m < M; m += 32) {
+            const double2 v = A[m * N + j];
+            const double a = hypot(v.x, v.y);
+            acc += (p == 2.0) ? a * a : pow(a, p);
+        }
+        for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) out[j] = (p == 2.0) ? sqrt(acc) : pow(acc, 1.0 / p);
+    }
+}
+
+// mutual coherence: max_{i != j} |<a_i, a_j>| / (|a_i| |a_j|); one CTA per column i
+__global__ void coherence_kernel(long long M, long long N, const double2* __restrict__ A,
+                                 const double* __restrict__ norms, unsigned long long* __restrict__ best_bits) {
+    __shared__ double red[32];
+    const long long i = blockIdx.x;
+    double best = 0.0;
+    for (long long j = threadIdx.x; j < N; j += blockDim.x) {
+        if (j == i) continue;
+        double sr = 0.0, si = 0.0;
+        for (long long m = 0; m < M; ++m) {
+            const double2 a = A[m * N + i], b = A[m * N + j];
+            sr += a.x * b.x + a.y * b.y;          // conj(a) * b
+            si += a.x * b.y - a.y * b.x;
+        }
+        const double c = hypot(sr, si) / (norms[i] * norms[j]);
+        best = fmax(best, c);
+    }
+    for (int off = 16; off; off >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        for (int off = 16; off; off >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, off));
+        // non-negative doubles order like their bit patterns
+        if (threadIdx.x == 0) atomicMax(best_bits, (unsigned long long)__double_as_longlong(best));
+    }
+}
+
+static unsigned grid_for(long long items, int threads) {
+    long long b = ceil_div(items, threads);
+    const long long cap = (long long)sm_count() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+}  // namespace sfa
+
+using namespace sfa;
+
+extern "C" int sfa_legendre_matrix(int N, int64_t Q, const double* ctheta, sfa_c128* L, void* stream) {
+    if (N < 0 || Q < 0) return SFA_ERR_INVALID;
+    if (Q == 0) return SFA_OK;
+    if (!ctheta || !L) return SFA_ERR_INVALID;
+    legendre_matrix_kernel<<<grid_for(Q, 256), 256, 0, (cudaStream_t)stream>>>(N, Q, ctheta, reinterpret_cast<double2*>(L));
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+extern "C" int sfa_matdiagmul(int64_t K, int64_t M, int64_t N, const sfa_c128* A, const sfa_c128* b, sfa_c128* C,
+                              void* stream) {
+    if (K < 0 || M < 0 || N < 0) return SFA_ERR_INVALID;
+    if (K * M * N == 0) return SFA_OK;
+    if (!A || !b || !C) return SFA_ERR_INVALID;
+    matdiagmul_kernel<<<grid_for(K * M * N, 256), 256, 0, (cudaStream_t)stream>>>(
+        K, M, N, reinterpret_cast<const double2*>(A), reinterpret_cast<const double2*>(b), reinterpret_cast<double2*>(C));
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+extern "C" int sfa_norm_of_columns(int64_t M, int64_t N, const sfa_c128* A, double p, double* out, void* stream) {
+    if (M < 0 || N < 0 || p <= 0.0) return SFA_ERR_INVALID;
+    if (N == 0) return SFA_OK;
+    if (!A || !out) return SFA_ERR_INVALID;
+    norm_of_columns_kernel<<<grid_for(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        M, N, reinterpret_cast<const double2*>(A), p, out);
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+// norms: scratch [N] doubles; result: one double (device)
+extern "C" int sfa_coherence_of_columns(int64_t M, int64_t N, const sfa_c128* A, double* norms, double* result,
+                                        void* stream) {
+    if (M < 0 || N < 0) return SFA_ERR_INVALID;
+    if (!result) return SFA_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    SFA_CUDA_CHECK(cudaMemsetAsync(result, 0, sizeof(double), st));
+    if (N == 0 || M == 0) return SFA_OK;
+    if (!A || !norms) return SFA_ERR_INVALID;
+    norm_of_columns_kernel<<<grid_for(N * 32, 256), 256, 0, st>>>(M, N, reinterpret_cast<const double2*>(A), 2.0, norms);
+    SFA_LAUNCH_CHECK();
+    coherence_kernel<<<(unsigned)N, 128, 0, st>>>(M, N, reinterpret_cast<const double2*>(A), norms,
+                                                   reinterpret_cast<unsigned long long*>(result));
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}

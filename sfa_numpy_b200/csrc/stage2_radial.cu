@@ -267,8 +267,14 @@ extern "C" int sfa_radial_filter(int kind, int N, int64_t F, const double* k, do
     const int scale = family ? kind - SFA_CIRC_WEIGHTS : kind;
     const int C = family ? 2 * N + 1 : N + 1;
     const int Cp = C | 1;
-    const int T = kRadialThreads;
-    const size_t smem = (size_t)T * Cp * sizeof(double2) + (size_t)(scale == 2 ? 2 : 1) * (N + 3) * T * sizeof(double);
+    // rows per CTA: as many as fit in shared memory (large orders, e.g. the examples' N = 50 circle
+    // with 101 columns, run with narrower CTAs)
+    int T = kRadialThreads;
+    size_t smem = 0;
+    for (;; T >>= 1) {
+        smem = (size_t)T * Cp * sizeof(double2) + (size_t)(scale == 2 ? 2 : 1) * (N + 3) * T * sizeof(double);
+        if (smem <= 200 * 1024 || T == 32) break;
+    }
     if (smem > 220 * 1024) return SFA_ERR_UNSUPPORTED;
     const double alpha = (method == SFA_REG_TIKH) ? tikh_alpha(a0) : 0.0;
     double* hr;

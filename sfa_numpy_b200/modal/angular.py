@@ -72,6 +72,21 @@ def cht_matrix(N, pol, weights=None):
     return Psi
 
 
+def Legendre_matrix(N, ctheta):
+    """Matrix of weighted Legendre polynomials ``(2n+1)/(4 pi) P_n(ctheta)``, shape (N+1, Q), complex
+    (reference: angular.py:73-103, which evaluates the coefficient form with np.polyval; here the
+    stable three-term recurrence)."""
+    lib = _lib.require_cuda()
+    dev = _device_of(ctheta)
+    x = asarray_1d(ctheta, dev)
+    Q = x.numel()
+    N = int(N)
+    L = torch.empty((N + 1, Q), dtype=torch.complex128, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sfa_legendre_matrix(N, Q, _lib.ptr(x), _lib.ptr(L), _lib.stream_ptr(dev)))
+    return L
+
+
 # ---------------------------------------------------------------------------
 # Sampling grids: host-side, run once, O(Q) (reference: angular.py:153-235).
 # ---------------------------------------------------------------------------

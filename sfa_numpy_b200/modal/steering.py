@@ -95,6 +95,22 @@ def pwd(Y_look, dn, Y_mic, p, precision=None, form="auto", out=None):
     return out
 
 
+def synthesize(Y_mic, bn, Y_src, precision="c128"):
+    """Forward model of the examples: ``p = matmul(matmul(Y_p, D), conj(Y_pw.T))`` with
+    ``D = diagonal_mode_mat(bn)`` (doc/examples/modal_beamforming_rigid_spherical_array.py:21-25) --
+    the pressure at the microphones for unit sources at the directions of ``Y_src``.
+    Returns (F, Q, S).  Same kernels as `pwd` (the sources play the role of the microphones and the
+    "spectra" are the identity)."""
+    dev = _device_of(Y_mic, bn, Y_src)
+    Y_src = as_complex_tensor(Y_src, dev)
+    bn_t = as_complex_tensor(bn, dev)
+    F = 1 if bn_t.ndim == 1 else bn_t.shape[0]
+    S_ = Y_src.shape[0]
+    cdtype = torch.complex128 if precision == "c128" else torch.complex64
+    eye = torch.eye(S_, dtype=cdtype, device=dev).expand(F, S_, S_).contiguous()
+    return pwd(Y_mic, bn_t, Y_src, eye, precision=precision)
+
+
 class PwdPlan:
     """Reusable device-side plan: workspace allocated once, operators kept resident."""
 

@@ -32,7 +32,7 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden():
     return {name: np.load(os.path.join(GOLDEN, name + ".npz"))
-            for name in ("angular", "radial", "pwd", "examples")}
+            for name in ("angular", "radial", "pwd", "examples", "extras")}
 
 
 def rel_err(x, ref, floor=1e-15):

@@ -187,7 +187,30 @@ def golden_examples():
     save("examples", **out)
 
 
+def golden_extras():
+    """SURVEY 8f "next" rows: Legendre_matrix and the util helpers."""
+    from micarray import util
+    out = {}
+    rng = np.random.default_rng(9)
+    ct = np.cos(np.linspace(0, np.pi, 41))
+    out["leg_ct"] = ct
+    out["leg12"] = angular.Legendre_matrix(12, ct)
+    A = rng.standard_normal((7, 5)) + 1j * rng.standard_normal((7, 5))
+    b = rng.standard_normal((3, 5)) + 1j * rng.standard_normal((3, 5))
+    out["mdm_A"], out["mdm_b"] = A, b
+    out["mdm_C"] = util.matdiagmul(A, b)
+    out["mdm_C1"] = util.matdiagmul(A, b[0])
+    out["noc2"] = util.norm_of_columns(A)
+    out["noc1"] = util.norm_of_columns(A, p=1)
+    out["coh"] = np.asarray(util.coherence_of_columns(A))
+    Y = angular.sht_matrix(3, *angular.grid_gauss(3)[:2])
+    out["coh_Y"] = np.asarray(util.coherence_of_columns(Y))
+    out["coh_Y_in"] = Y
+    save("extras", **out)
+
+
 if __name__ == "__main__":
+    golden_extras()
     golden_angular()
     golden_radial()
     golden_pwd()

@@ -181,3 +181,15 @@ def test_identities_mpmath():
         hd = mp.diff(h, x)
         ref = complex(-1j / (x ** 2 * hd))
         assert abs(b[nn] - ref) <= 1e-12 * abs(ref)
+
+
+def test_extras(golden):
+    """SURVEY 8f "next" rows against the unmodified reference."""
+    g = golden["extras"]
+    assert_close(O.Legendre_matrix(12, g["leg_ct"]), g["leg12"], **EXACT)
+    assert_close(O.matdiagmul(g["mdm_A"], g["mdm_b"]), g["mdm_C"], **EXACT)
+    assert_close(O.matdiagmul(g["mdm_A"], g["mdm_b"][0]), g["mdm_C1"], **EXACT)
+    assert_close(O.norm_of_columns(g["mdm_A"]), g["noc2"], **TIGHT)
+    assert_close(O.norm_of_columns(g["mdm_A"], 1), g["noc1"], **TIGHT)
+    assert abs(O.coherence_of_columns(g["mdm_A"]) - float(g["coh"])) < 1e-14
+    assert abs(O.coherence_of_columns(g["coh_Y_in"]) - float(g["coh_Y"])) < 1e-14
