@@ -222,7 +222,7 @@ def main():
     d_azl, d_coll = torch.from_numpy(azl).to(dev), torch.from_numpy(col).to(dev)
     d_k = torch.from_numpy(k).to(dev)
     X = torch.from_numpy(Xh).to(dev)
-    out = torch.empty((F, L, T), dtype=torch.complex64, device=dev)
+    out = S.empty_beams(F, L, T, torch.complex64, dev)
     plan = {}
 
     def step():

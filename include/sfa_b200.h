@@ -157,6 +157,9 @@ typedef struct {
     int d_is_per_order;
     int precision;         /* enum sfa_precision                                    */
     int form;              /* 0 = auto, 1 = steering matrix A_f then A_f X_f, 2 = factored (two GEMMs) */
+    int64_t out_ld;        /* row pitch of `out` in elements (0 = T, i.e. contiguous [F, L, T]).  A pitch that
+                              is a multiple of 32 frames (256 B) is worth ~1.4x of HBM write bandwidth: every
+                              128-byte line of a row tile then belongs to one CTA                            */
 } sfa_pwd_shape;
 
 size_t sfa_pwd_work_bytes(const sfa_pwd_shape* s);

@@ -319,7 +319,7 @@ static long long gcdll(long long a, long long b) { return b ? gcdll(b, a % b) : 
 
 struct Plan {
     int form;
-    long long Qp, Mp, Tld;      // padded k extents / leading dims
+    long long Qp, Mp, Tld, Old; // padded k extents / leading dims (Z rows, out rows)
     int ngroups;
     long long fc;               // bins per chunk
     size_t off_G, off_A, off_dF, off_P1, off_P2, off_dcols, off_Z, total, a_slab;
@@ -348,7 +348,12 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
     const bool c64 = is_c64(s);
     p->Qp = round_up(s->Q, 4);
     p->Mp = round_up(s->M, 4);
-    p->Tld = s->T;
+    // Row pitches that are multiples of 32 frames (256 B) keep every 128-byte line of a tile row inside
+    // one CTA's tile; with an unaligned pitch (T = 938 -> 7504 B) the lines at tile edges are shared by
+    // two CTAs and HBM absorbs the partial-line writes at 3.3 instead of 4.9 TB/s (tools/store_probe2.cu).
+    p->Tld = (s->T > 128) ? round_up(s->T, 32) : s->T;
+    p->Old = s->out_ld > 0 ? s->out_ld : s->T;
+    if (p->Old < s->T) return SFA_ERR_INVALID;
     p->ngroups = s->Cd;
     int form = s->form;
     if (form == 0) {
@@ -461,7 +466,7 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
             SFA_LAUNCH_CHECK();
             rc = launch_steer_build(G, dF, Cd, 0, (int)nf, LQ, is_hybrid(s), A, st);
             if (rc != SFA_OK) return rc;
-            return cgemm_splitk(nf, L, T, Q, A, p.Qp, 0, x, T, Q * T, o, T, L * T, nullptr, 0, is_hybrid(s), st);
+            return cgemm_splitk(nf, L, T, Q, A, p.Qp, 0, x, T, Q * T, o, p.Old, L * p.Old, nullptr, 0, is_hybrid(s), st);
         }
         const float* P1 = reinterpret_cast<const float*>(w + p.off_P1);
         const float* P2 = reinterpret_cast<const float*>(w + p.off_P2);
@@ -471,7 +476,7 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
         SFA_LAUNCH_CHECK();
         rc = cgemm_splitk(nf, M, T, Q, P1, p.Qp, 1, x, T, Q * T, Z, p.Tld, (long long)M * p.Tld, dcols, M, is_hybrid(s), st);
         if (rc != SFA_OK) return rc;
-        return cgemm_splitk(nf, L, T, M, P2, p.Mp, 1, Z, p.Tld, (long long)M * p.Tld, o, T, L * T, nullptr, 0, is_hybrid(s), st);
+        return cgemm_splitk(nf, L, T, M, P2, p.Mp, 1, Z, p.Tld, (long long)M * p.Tld, o, p.Old, L * p.Old, nullptr, 0, is_hybrid(s), st);
     }
     const double2* x = reinterpret_cast<const double2*>(X);
     double2* o = reinterpret_cast<double2*>(out);
@@ -481,7 +486,7 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
         steer_build_f64_kernel<<<grid1d(LQ * nf), 256, 0, st>>>(G, dd, Cd, Cd, 0, (int)nf, LQ, A);
         SFA_LAUNCH_CHECK();
         zgemm_kernel<<<zgrid(nf * ceil_div(T, 64) * ceil_div(L, 64)), 256, 0, st>>>(
-            nf, L, T, Q, A, p.Qp, LQ, x, T, Q * T, o, T, L * T, nullptr, 0);
+            nf, L, T, Q, A, p.Qp, LQ, x, T, Q * T, o, p.Old, L * p.Old, nullptr, 0);
         SFA_LAUNCH_CHECK();
         return SFA_OK;
     }
@@ -494,7 +499,7 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
         nf, M, T, Q, P1, Q, 0, x, T, Q * T, Z, p.Tld, (long long)M * p.Tld, dcols, M);
     SFA_LAUNCH_CHECK();
     zgemm_kernel<<<zgrid(nf * ceil_div(T, 64) * ceil_div(L, 64)), 256, 0, st>>>(
-        nf, L, T, M, yl, M, 0, Z, p.Tld, (long long)M * p.Tld, o, T, L * T, nullptr, 0);
+        nf, L, T, M, yl, M, 0, Z, p.Tld, (long long)M * p.Tld, o, p.Old, L * p.Old, nullptr, 0);
     SFA_LAUNCH_CHECK();
     return SFA_OK;
 }
@@ -548,7 +553,7 @@ static int pwd_steering_pipelined(const sfa_pwd_shape* s, const Plan& p, const d
         }
         SFA_CUDA_CHECK(cudaEventRecord(ss->built[slot], ss->stream));
         SFA_CUDA_CHECK(cudaStreamWaitEvent(st, ss->built[slot], 0));
-        int rc = cgemm_splitk(nf, L, T, Q, Aslab[slot], p.Qp, 0, x + f0 * Q * T, T, Q * T, o + f0 * L * T, T, L * T,
+        int rc = cgemm_splitk(nf, L, T, Q, Aslab[slot], p.Qp, 0, x + f0 * Q * T, T, Q * T, o + f0 * L * p.Old, p.Old, L * p.Old,
                               nullptr, 0, is_hybrid(s), st);
         if (rc != SFA_OK) return rc;
         SFA_CUDA_CHECK(cudaEventRecord(ss->done[slot], st));
@@ -590,7 +595,7 @@ extern "C" int sfa_pwd_apply(const sfa_pwd_shape* s, const sfa_c128* Y_L, const 
         const long long nf = (s->F - f0 < p.fc) ? (s->F - f0) : p.fc;
         rc = pwd_run_bins(s, p, nf, yl, dd + f0 * s->Cd,
                           reinterpret_cast<const unsigned char*>(X) + (size_t)f0 * s->Q * s->T * eb,
-                          reinterpret_cast<unsigned char*>(out) + (size_t)f0 * s->L * s->T * eb, w, st);
+                          reinterpret_cast<unsigned char*>(out) + (size_t)f0 * s->L * p.Old * eb, w, st);
         if (rc != SFA_OK) return rc;
     }
     return SFA_OK;
@@ -616,6 +621,8 @@ extern "C" int sfa_pwd_host_create(sfa_pwd_host_ctx** out_ctx, const sfa_pwd_sha
     SFA_CUDA_CHECK(cudaSetDevice(device));
     sfa_pwd_host_ctx* c = new sfa_pwd_host_ctx();
     c->shape = *s;
+    c->shape.out_ld = (s->T > 128) ? round_up(s->T, 32) : s->T;     // device-side row pitch of the beams
+    s = &c->shape;
     int rc = make_plan(s, &c->plan);
     if (rc != SFA_OK) {
         delete c;
@@ -635,7 +642,7 @@ extern "C" int sfa_pwd_host_create(sfa_pwd_host_ctx** out_ctx, const sfa_pwd_sha
         SFA_CUDA_CHECK(cudaEventCreateWithFlags(&c->cmp_done[i], cudaEventDisableTiming));
         SFA_CUDA_CHECK(cudaEventCreateWithFlags(&c->out_done[i], cudaEventDisableTiming));
         SFA_CUDA_CHECK(cudaMalloc(&c->d_X[i], (size_t)chunk * s->Q * s->T * eb));
-        SFA_CUDA_CHECK(cudaMalloc(&c->d_O[i], (size_t)chunk * s->L * s->T * eb));
+        SFA_CUDA_CHECK(cudaMalloc(&c->d_O[i], (size_t)chunk * s->L * s->out_ld * eb));
     }
     SFA_CUDA_CHECK(cudaMalloc(&c->d_YL, (size_t)s->L * s->M * 16));
     SFA_CUDA_CHECK(cudaMalloc(&c->d_YQ, (size_t)s->Q * s->M * 16));
@@ -669,6 +676,7 @@ extern "C" int sfa_pwd_host_run(sfa_pwd_host_ctx* c, const void* X_host, void* o
     const size_t eb = elem_bytes(s);
     unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)c->d_work + 255) & ~(uintptr_t)255);
     const size_t x_bin = (size_t)s->Q * s->T * eb, o_bin = (size_t)s->L * s->T * eb;
+    const size_t o_bin_dev = (size_t)s->L * s->out_ld * eb;        // padded rows on the device
     int slot = 0;
     long long it = 0;
     for (long long f0 = 0; f0 < s->F; f0 += c->chunk, ++it, slot ^= 1) {
@@ -685,13 +693,15 @@ extern "C" int sfa_pwd_host_run(sfa_pwd_host_ctx* c, const void* X_host, void* o
             const long long ng = (nf - g0 < c->plan.fc) ? (nf - g0) : c->plan.fc;
             int rc = pwd_run_bins(s, c->plan, ng, reinterpret_cast<const double2*>(c->d_YL),
                                   reinterpret_cast<const double2*>(c->d_d) + (f0 + g0) * s->Cd,
-                                  c->d_X[slot] + g0 * x_bin, c->d_O[slot] + g0 * o_bin, w, c->s_cmp);
+                                  c->d_X[slot] + g0 * x_bin, c->d_O[slot] + g0 * o_bin_dev, w, c->s_cmp);
             if (rc != SFA_OK) return rc;
         }
         SFA_CUDA_CHECK(cudaEventRecord(c->cmp_done[slot], c->s_cmp));
         SFA_CUDA_CHECK(cudaStreamWaitEvent(c->s_out, c->cmp_done[slot], 0));
-        SFA_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(out_host) + f0 * o_bin, c->d_O[slot],
-                                       nf * o_bin, cudaMemcpyDeviceToHost, c->s_out));
+        // rows are compacted by the copy engine (device pitch out_ld -> host pitch T)
+        SFA_CUDA_CHECK(cudaMemcpy2DAsync(reinterpret_cast<unsigned char*>(out_host) + f0 * o_bin, (size_t)s->T * eb,
+                                         c->d_O[slot], (size_t)s->out_ld * eb, (size_t)s->T * eb,
+                                         (size_t)nf * s->L, cudaMemcpyDeviceToHost, c->s_out));
         SFA_CUDA_CHECK(cudaEventRecord(c->out_done[slot], c->s_out));
     }
     SFA_CUDA_CHECK(cudaStreamSynchronize(c->s_out));

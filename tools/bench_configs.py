@@ -24,7 +24,7 @@ for name in sorted(CONFIGS):
     X = torch.randn((F, Q, T), dtype=torch.complex64, device="cuda")
     for prec in ("c64", "c64_fast"):
         plan = S.PwdPlan(Y_q, dn, Y_p, T, precision=prec)
-        out = torch.empty(plan.out_shape, dtype=torch.complex64, device="cuda")
+        out = S.empty_beams(*plan.out_shape, torch.complex64, torch.device("cuda"))
         for _ in range(2):
             plan(X, out=out)
         torch.cuda.synchronize()

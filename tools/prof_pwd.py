@@ -21,7 +21,7 @@ Y_q = A.sht_matrix(N, azl, col)
 _, dn, _ = R.radial_filters(N, k, 0.042, "rigid", 100.0, "Tikh")
 X = torch.from_numpy(O.synth_spectra(F, 64, T, seed=0)).cuda()
 plan = S.PwdPlan(Y_q, dn, Y_p, T, precision=PREC)
-out = torch.empty((F, L, T), dtype=torch.complex64, device="cuda")
+out = S.empty_beams(F, L, T, torch.complex64, torch.device("cuda"))
 for _ in range(3):
     plan(X, out=out)
 torch.cuda.synchronize()
