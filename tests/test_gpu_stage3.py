@@ -223,7 +223,12 @@ def test_pwd_linearity_and_plan(mic):
 def test_pwd_host_path(mic):
     """NumPy in / NumPy out through sfa_pwd_host_* (chunked H2D / compute / D2H pipeline)."""
     S = mic.modal.steering
-    N, Q, L, F, T = 4, 50, 200, 37, 70
+    for T in (70, 138):                  # 138 > 128 and not a multiple of 32: row-padded device buffer + 2-D D2H copy
+        _host_path_case(S, T)
+
+
+def _host_path_case(S, T):
+    N, Q, L, F = 4, 50, 200, 37
     az, co, w = O.grid_gauss(N)
     azl, col, _ = O.fibonacci_grid(L)
     Yp_ref, Yq_ref = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
