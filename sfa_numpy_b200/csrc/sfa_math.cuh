@@ -225,36 +225,37 @@ SFA_HD void cyl_jn_array(int nmax, double x, dvec J, double* Y0, double* Y1) {
     }
     const double ix2 = 2.0 / x;
     int n = miller_start(nmax < 1 ? 1 : nmax, x);
-    if (n & 1) ++n;                      // start on an even order
-    double fp = 0.0, f = 1.0e-30;        // f = f_n, fp = f_{n+1}
+    if (n & 1) ++n;                      // start on an even order 2K
+    // Two orders per iteration: fe = f_{2k} (even), fo = f_{2k+1} (the odd order above it).
+    // The Y_1 weight (2k+1)/(k(k+1)) = 1/k + 1/(k+1), so ONE division (1/k) serves both series.
+    double fe = 1.0e-30, fo = 0.0;
     double sum_even = 0.0;               // sum_{k>=1} f_{2k}
     double sum_y0 = 0.0;                 // sum (-1)^k f_{2k}/k
-    double sum_y1 = 0.0;                 // sum (-1)^k (2k+1)/(k(k+1)) f_{2k+1}
-    for (; n >= 1; --n) {
-        // account for f_n
-        if ((n & 1) == 0) {
-            const int k = n >> 1;
-            sum_even += f;
-            sum_y0 += ((k & 1) ? -f : f) / (double)k;
-        } else if (n >= 3) {
-            const int k = (n - 1) >> 1;
-            const double w = (double)(2 * k + 1) / ((double)k * (double)(k + 1));
-            sum_y1 += ((k & 1) ? -f : f) * w;
-        }
-        if (n <= nmax) J[n] = f;
-        const double t = (double)n * ix2 * f - fp;   // f_{n-1}
-        fp = f;
-        f = t;
-        if (fabs(f) > kRescaleHi) {
-            f *= kRescaleLo;
-            fp *= kRescaleLo;
+    double sum_y1 = 0.0;                 // sum (-1)^k (1/k + 1/(k+1)) f_{2k+1}
+    double rk1 = 0.0;                    // 1/(k+1)
+    for (int k = n >> 1; k >= 1; --k) {
+        const double rk = 1.0 / (double)k;
+        const double sg = (k & 1) ? -1.0 : 1.0;
+        sum_y1 += sg * fo * (rk + rk1);
+        sum_even += fe;
+        sum_y0 += sg * fe * rk;
+        const double f_odd = (double)(2 * k) * ix2 * fe - fo;             // f_{2k-1}
+        const double f_even = (double)(2 * k - 1) * ix2 * f_odd - fe;     // f_{2k-2}
+        fo = f_odd;
+        fe = f_even;
+        rk1 = rk;
+        if (2 * k - 1 <= nmax) J[2 * k - 1] = fo;
+        if (2 * k - 2 <= nmax) J[2 * k - 2] = fe;
+        if (fabs(fe) > kRescaleHi || fabs(fo) > kRescaleHi) {
+            fe *= kRescaleLo;
+            fo *= kRescaleLo;
             sum_even *= kRescaleLo;
             sum_y0 *= kRescaleLo;
             sum_y1 *= kRescaleLo;
-            for (int q = n; q <= nmax; ++q) J[q] *= kRescaleLo;
+            for (int q = 2 * k - 2; q <= nmax; ++q) J[q] *= kRescaleLo;
         }
     }
-    J[0] = f;                            // f_0 (fp = f_1)
+    const double f = fe, fp = fo;        // f_0, f_1
     const double norm = 1.0 / (f + 2.0 * sum_even);
     for (int q = 0; q <= nmax; ++q) J[q] *= norm;
     const double j0 = f * norm, j1 = fp * norm;
