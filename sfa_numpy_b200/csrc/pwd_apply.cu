@@ -24,6 +24,14 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
                    long long strideO, int out_mode, const float2* rowscale, long long strideS, int hybrid,
                    cudaStream_t st);
 
+int launch_cgemm3x_kloop(long long B, long long Nn, long long Mm, long long K, const float* Pplanar, long long Kp,
+                         const float2* R, long long ldR, long long strideR, float2* out, long long ldo,
+                         long long strideO, const float2* rowscale, long long strideS, int hybrid,
+                         void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t cgemm3x_kloop_scratch_bytes(long long K, int hybrid);
+
+static inline bool use_kloop(long long K, int p_shared) { return K > 64 && p_shared && !getenv("SFA_NO_KLOOP"); }
+
 constexpr int kOutC64 = 0, kOutFirstOfMany = 1, kOutAccum = 2;
 
 __device__ __forceinline__ uint32_t tf32_rna(float x) {
@@ -322,7 +330,7 @@ struct Plan {
     long long Qp, Mp, Tld, Old; // padded k extents / leading dims (Z rows, out rows)
     int ngroups;
     long long fc;               // bins per chunk
-    size_t off_G, off_A, off_dF, off_P1, off_P2, off_dcols, off_Z, total, a_slab;
+    size_t off_G, off_A, off_dF, off_P1, off_P2, off_dcols, off_Z, off_scratch, scratch_bytes, total, a_slab;
 };
 
 static inline bool is_c64(const sfa_pwd_shape* s) {
@@ -330,8 +338,14 @@ static inline bool is_c64(const sfa_pwd_shape* s) {
 }
 static inline int is_hybrid(const sfa_pwd_shape* s) { return s->precision == SFA_PREC_C64_TF32_BF16 ? 1 : 0; }
 
-static double gemm_cost(double Nn, double Mm, double K, double batches) {
-    // MMA work in padded tile units plus the split-K read-modify-write traffic, in seconds (rough).
+static double gemm_cost(double Nn, double Mm, double K, double batches, bool p_shared) {
+    // Rough seconds per chunk of `batches` bins: MMA work in padded tile units plus output traffic.
+    if (use_kloop((long long)K, p_shared ? 1 : 0)) {
+        // in-kernel K loop (cgemm3x_kloop_sm100.cu): folded (batch, m) rows, 128-row n tiles, one output pass
+        const double mma = ceil(batches * Mm / 128.0) * 128.0 * ceil(Nn / 128.0) * 128.0 * ceil(K / 32.0) * 32.0 * 8.0 * 3.0;
+        return mma / 600e12 + batches * Nn * Mm * 8.0 / 5.0e12;
+    }
+    // resident-K kernel (cgemm3x_sm100.cu): one launch and one read-modify-write of the output per 64-wide K chunk
     const double mma = ceil(Mm / 128.0) * 128.0 * ceil(Nn / 64.0) * 64.0 * ceil(K / 8.0) * 8.0 * 8.0 * 3.0;
     const double chunks = ceil(K / 64.0);
     const double bytes = Nn * Mm * 8.0 * (1.0 + 2.0 * (chunks - 1.0));
@@ -357,10 +371,11 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
     p->ngroups = s->Cd;
     int form = s->form;
     if (form == 0) {
-        const double c1 = gemm_cost((double)s->L, (double)s->T, (double)s->Q, 1.0) +
-                          (double)s->L * p->Qp * (16.0 * 2.0 / 6.0e12 + 8.0 * s->Cd / 40e12);
-        const double c2 = gemm_cost((double)s->M, (double)s->T, (double)s->Q, 1.0) +
-                          gemm_cost((double)s->L, (double)s->T, (double)s->M, 1.0);
+        const double nb = 64.0;      // compare per 64 bins (the folded K-loop tiles span several bins)
+        const double c1 = gemm_cost((double)s->L, (double)s->T, (double)s->Q, nb, false) +
+                          nb * (double)s->L * p->Qp * (16.0 * 2.0 / 6.0e12 + 8.0 * s->Cd / 40e12);
+        const double c2 = gemm_cost((double)s->M, (double)s->T, (double)s->Q, nb, true) +
+                          gemm_cost((double)s->L, (double)s->T, (double)s->M, nb, true);
         form = (c1 <= c2 && s->Cd <= 64) ? 1 : 2;
     }
     if (form == 1 && s->Cd > 64) return SFA_ERR_UNSUPPORTED;
@@ -379,6 +394,7 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
     p->fc = fc;
     size_t off = 0;
     p->off_G = p->off_A = p->off_dF = p->off_P1 = p->off_P2 = p->off_dcols = p->off_Z = p->a_slab = 0;
+    p->off_scratch = p->scratch_bytes = 0;
     const size_t esz = c64 ? 8 : 16;
     if (form == 1) {
         p->off_G = off;
@@ -397,6 +413,13 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
         off += align_up((size_t)fc * s->M * esz);
         p->off_Z = off;
         off += align_up((size_t)fc * s->M * p->Tld * esz);
+        if (c64) {                                           // partial-sum slots of the in-kernel K loop
+            size_t a = use_kloop(s->Q, 1) ? cgemm3x_kloop_scratch_bytes(s->Q, is_hybrid(s)) : 0;
+            size_t b = use_kloop(s->M, 1) ? cgemm3x_kloop_scratch_bytes(s->M, is_hybrid(s)) : 0;
+            p->scratch_bytes = a > b ? a : b;
+            p->off_scratch = off;
+            off += align_up(p->scratch_bytes);
+        }
     }
     p->total = off + 256;
     return SFA_OK;
@@ -404,7 +427,12 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
 
 static int cgemm_splitk(long long B, long long Nn, long long Mm, long long K, const float* Pp, long long Kp,
                         int p_shared, const float2* R, long long ldR, long long strideR, float2* out, long long ldo,
-                        long long strideO, const float2* rowscale, long long strideS, int hybrid, cudaStream_t st) {
+                        long long strideO, const float2* rowscale, long long strideS, int hybrid, cudaStream_t st,
+                        void* scratch = nullptr, size_t scratch_bytes = 0) {
+    // long inner dimension with a shared left operand (factored form): one launch, K loop in the kernel
+    if (use_kloop(K, p_shared))
+        return launch_cgemm3x_kloop(B, Nn, Mm, K, Pp, Kp, R, ldR, strideR, out, ldo, strideO, rowscale, strideS, hybrid,
+                                    scratch, scratch_bytes, st);
     for (long long k0 = 0; k0 < K; k0 += 64) {
         const int kc = (int)((K - k0 < 64) ? (K - k0) : 64);
         // the first pass of a split-K product is marked too, so that every pass uses the same (unfolded) tiling
@@ -474,9 +502,11 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
         float2* Z = reinterpret_cast<float2*>(w + p.off_Z);
         expand_diag_kernel<float2><<<grid1d(nf * M), 256, 0, st>>>(dd, nf, Cd, M, s->d_is_per_order, dcols);
         SFA_LAUNCH_CHECK();
-        rc = cgemm_splitk(nf, M, T, Q, P1, p.Qp, 1, x, T, Q * T, Z, p.Tld, (long long)M * p.Tld, dcols, M, is_hybrid(s), st);
+        rc = cgemm_splitk(nf, M, T, Q, P1, p.Qp, 1, x, T, Q * T, Z, p.Tld, (long long)M * p.Tld, dcols, M, is_hybrid(s), st,
+                          w + p.off_scratch, p.scratch_bytes);
         if (rc != SFA_OK) return rc;
-        return cgemm_splitk(nf, L, T, M, P2, p.Mp, 1, Z, p.Tld, (long long)M * p.Tld, o, p.Old, L * p.Old, nullptr, 0, is_hybrid(s), st);
+        return cgemm_splitk(nf, L, T, M, P2, p.Mp, 1, Z, p.Tld, (long long)M * p.Tld, o, p.Old, L * p.Old, nullptr, 0, is_hybrid(s), st,
+                            w + p.off_scratch, p.scratch_bytes);
     }
     const double2* x = reinterpret_cast<const double2*>(X);
     double2* o = reinterpret_cast<double2*>(out);
@@ -775,10 +805,14 @@ extern "C" int sfa_cgemm3x(int64_t B, int64_t Nn, int64_t Mm, int64_t K, const s
                                                                    pb, Nn, K, Kp, hybrid, Pp);
     int rc = SFA_OK;
     if (cudaGetLastError() != cudaSuccess) rc = SFA_ERR_CUDA;
+    void* scratch = nullptr;
+    const size_t sb = use_kloop(K, strideP == 0) ? cgemm3x_kloop_scratch_bytes(K, hybrid) : 0;
+    if (sb) SFA_CUDA_CHECK(cudaMallocAsync(&scratch, sb, st));
     if (rc == SFA_OK)
         rc = cgemm_splitk(B, Nn, Mm, K, Pp, Kp, strideP == 0, reinterpret_cast<const float2*>(R), ldR, strideR,
                           reinterpret_cast<float2*>(out), ldo, strideO, reinterpret_cast<const float2*>(rowscale),
-                          strideS, hybrid, st);
+                          strideS, hybrid, st, scratch, sb);
+    if (scratch) cudaFreeAsync(scratch, st);
     cudaFreeAsync(Pp, st);
     return rc;
 }

@@ -22,8 +22,13 @@ for name in sorted(CONFIGS):
         _, dn, _ = R.radial_filters(N, O.wavenumbers(F) + 0.1, r, setup, a0, method, kind="circular_pw")
     Q = Y_p.shape[0]
     X = torch.randn((F, Q, T), dtype=torch.complex64, device="cuda")
-    for prec in ("c64", "c64_fast"):
-        plan = S.PwdPlan(Y_q, dn, Y_p, T, precision=prec)
+    forms = sys.argv[1].split(",") if len(sys.argv) > 1 else ["auto"]
+    for prec, form in [(p_, f_) for p_ in ("c64", "c64_fast") for f_ in forms]:
+        try:
+            plan = S.PwdPlan(Y_q, dn, Y_p, T, precision=prec, form=form)
+        except Exception as e:          # e.g. steering form with more than 64 groups
+            print(json.dumps({"config": name, "precision": prec, "form": form, "error": str(e)[:80]}))
+            continue
         out = S.empty_beams(*plan.out_shape, torch.complex64, torch.device("cuda"))
         for _ in range(2):
             plan(X, out=out)
@@ -36,7 +41,7 @@ for name in sorted(CONFIGS):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
-        print(json.dumps({"config": name, "N": N, "Q": Q, "F": F, "L": L, "T": T, "precision": prec, "form": plan.shape.form,
+        print(json.dumps({"config": name, "N": N, "Q": Q, "F": F, "L": L, "T": T, "precision": prec, "form": form, "form_used": plan.shape.form,
                           "ms": round(ms, 3), "outputs_per_s": F * L * T / ms * 1e3}))
     del X, out, plan
     torch.cuda.empty_cache()
