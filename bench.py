@@ -327,6 +327,42 @@ def main():
                        "parallelism": "frequency-sharded x%d, no collective" % world},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
 
+    # ---- the collective of the multi-GPU path (north_star: "only an all-gather of the output beam maps") ----
+    # Not inside `value` (each rank's beams stay resident); timed separately with CUDA events, max over ranks:
+    #  (a) beam power map mean_t|q|^2 [F, L] f32 per rank (one HBM-read-bound kernel) + NCCL all-gather;
+    #  (b) NCCL all-gather of a bounded slab of the complex64 beam tensor itself (32 bins per rank).
+    try:
+        from sfa_numpy_b200 import dist as sdist
+
+        def timed(fn, n=3):
+            fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b) / n], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        pm_ms = timed(lambda: S.power_map(out))
+        coll = {"power_map_kernel_ms": pm_ms, "power_map_read_GBps": 8.0 * F * L * T / (pm_ms * 1e-3) / 1e9}
+        if world > 1:
+            coll["power_map_allgather_ms"] = timed(lambda: sdist.gather_power_map(out, world * F))
+            coll["power_map_allgather_bytes_per_rank"] = 4 * F * L
+            nb = 32
+            slab = out[:nb].contiguous()
+            ag_ms = timed(lambda: sdist.all_gather_slabs(slab, world * nb))
+            coll["beam_slab_allgather"] = {"bins_per_rank": nb, "bytes_per_rank": int(slab.numel() * 8), "ms": ag_ms,
+                                           "ingest_GBps_per_gpu": (world - 1) * slab.numel() * 8 / (ag_ms * 1e-3) / 1e9}
+            del slab
+        line["collective"] = coll
+    except Exception as e:
+        line["collective"] = {"error": repr(e)}
+
     # ---- e2e through the host-buffer C ABI: every rank pushes its own batch through its own PCIe link ----
     if not args.no_e2e:
         host, err = None, None

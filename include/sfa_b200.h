@@ -71,6 +71,8 @@ int sfa_device_info(int* sm_count, int* cc_major, int* cc_minor);
 long long sfa_launch_count(void);
 int sfa_prof_enable(int on);
 int sfa_prof_read(double* total_ms, long long* count);
+int sfa_prof_timeline(double* rows /* [max_rows][3] = kind, start_ms, end_ms */, int max_rows);
+int sfa_prof_span(double* span_ms);   /* first launch start -> last launch end (gaps = span - total) */
 
 /* ---- stage 1: angular matrices ------------------------------------------------ */
 
@@ -191,6 +193,11 @@ int sfa_pwd_host_destroy(sfa_pwd_host_ctx* ctx);
 /* pinned host memory helpers for the host path */
 int sfa_host_alloc(void** p, size_t bytes);
 int sfa_host_free(void* p);
+
+/* Beam power map mean_t |q[f,l,t]|^2 (what the reference's examples plot as db(q), e.g.
+ * doc/examples/modal_beamforming_rigid_spherical_array.py:43-57, and the all-gathered quantity of the
+ * multi-GPU path).  q: rows = F*L rows of T complex64 with row pitch ld (elements); out: [rows] float32. */
+int sfa_power_map(int64_t rows, int64_t T, int64_t ld, const sfa_c64* q, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsfa_b200.so")
+# tuning experiments: an alternative build of the same library (tools/ only)
+LIB_PATH = os.environ.get("SFA_B200_LIB", LIB_PATH)
 
 c_void_p, c_int, c_int64, c_double, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                                ctypes.c_double, ctypes.c_size_t)
@@ -31,6 +33,8 @@ SIGNATURES = {
     "sfa_launch_count": (ctypes.c_longlong, []),
     "sfa_prof_enable": (c_int, [c_int]),
     "sfa_prof_read": (c_int, [ctypes.POINTER(c_double), ctypes.POINTER(ctypes.c_longlong)]),
+    "sfa_prof_span": (c_int, [ctypes.POINTER(c_double)]),
+    "sfa_prof_timeline": (c_int, [ctypes.POINTER(c_double), c_int]),
     "sfa_sht_matrix": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "sfa_cht_matrix": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfa_radial_work_bytes": (c_size_t, [c_int, c_int, c_int64]),
@@ -53,6 +57,7 @@ SIGNATURES = {
     "sfa_pwd_host_set_operators": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfa_pwd_host_run": (c_int, [c_void_p, c_void_p, c_void_p]),
     "sfa_pwd_host_destroy": (c_int, [c_void_p]),
+    "sfa_power_map": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "sfa_host_alloc": (c_int, [ctypes.POINTER(c_void_p), c_size_t]),
     "sfa_host_free": (c_int, [c_void_p]),
 }

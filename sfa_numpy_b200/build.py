@@ -36,6 +36,7 @@ def source_hash():
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     h.update(b"debug" if os.environ.get("SFA_BUILD_DEBUG_HOOKS") else b"")
+    h.update(os.environ.get("SFA_BUILD_DEFS", "").encode())
     return h.hexdigest()
 
 
@@ -52,6 +53,7 @@ def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     extra = ["-DSFA_DEBUG_HOOKS"] if os.environ.get("SFA_BUILD_DEBUG_HOOKS") else []
+    extra += os.environ.get("SFA_BUILD_DEFS", "").split()          # tuning experiments, e.g. -DSFA_GEMM_STAGES=2
     tmp = LIB + ".tmp.%d" % os.getpid()
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)

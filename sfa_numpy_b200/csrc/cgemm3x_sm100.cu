@@ -50,7 +50,14 @@ namespace sfa {
 constexpr int kTileM = 128;          // m per task (TMEM lanes)
 constexpr int kTileN = 64;           // rows of P per MMA step
 constexpr int kMaxK = 64;            // complex k resident in TMEM per launch
-constexpr int kStagesB = 3;
+#ifndef SFA_GEMM_STAGES
+#define SFA_GEMM_STAGES 2
+#endif
+#ifndef SFA_GEMM_STORE_RING
+#define SFA_GEMM_STORE_RING 2
+#endif
+constexpr int kStagesB = SFA_GEMM_STAGES;
+constexpr int kStoreRing = SFA_GEMM_STORE_RING;          // staging buffers per epilogue half
 constexpr int kBoxK = 32;            // fp32 per 128-byte swizzle row
 constexpr int kBoxBytes = kTileN * kBoxK * 4;            // 8 KB
 constexpr int kStageBytes = 4 * 2 * kBoxBytes;           // 4 planes x 2 k-boxes = 64 KB
@@ -108,7 +115,7 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char* stage_base = smem;                                    // kStagesB x 64 KB
     unsigned char* store_base = smem + (size_t)kStagesB * kStageBytes;   // 2 x 16 KB epilogue staging
-    Barriers* bars = reinterpret_cast<Barriers*>(store_base + 2 * kStoreBytes);
+    Barriers* bars = reinterpret_cast<Barriers*>(store_base + 2 * kStoreRing * kStoreBytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -345,7 +352,7 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
         const int quarter = warp & 3;
         const int chalf = (warp - 6) >> 2;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        int acc = 0;
+        int acc = 0, ring = 0;
         uint32_t acc_phase = 0;
         for (long long grp = cluster_id; grp < n_groups; grp += n_clusters) {
             long long b = grp / prm.m_groups;
@@ -397,12 +404,13 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
                             }
                         }
                     }
-                    float2* sbuf = reinterpret_cast<float2*>(store_base + chalf * kStoreBytes) + quarter * 32 + lane;
                     const bool issuer = (quarter == 0) && (lane == 0);
 #pragma unroll
                     for (int part = 0; part < 2; ++part) {
-                        // the previous store from this buffer must have finished reading shared memory
-                        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        unsigned char* const ring_buf = store_base + (size_t)(chalf * kStoreRing + ring) * kStoreBytes;
+                        float2* sbuf = reinterpret_cast<float2*>(ring_buf) + quarter * 32 + lane;
+                        // the store that used this buffer kStoreRing parts ago must have finished reading shared memory
+                        if (issuer) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStoreRing - 1) : "memory");
                         named_bar_sync(1 + chalf, 128);
 #pragma unroll
                         for (int j = 0; j < kStoreRows; ++j)
@@ -411,10 +419,12 @@ cgemm3x_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant_
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         named_bar_sync(1 + chalf, 128);
                         if (issuer && ncols > part * kStoreRows) {
-                            tma_store_3d(&o_map, store_base + chalf * kStoreBytes, 2 * mt * kTileM,
+                            tma_store_3d(&o_map, ring_buf, 2 * mt * kTileM,
                                          (int)nbase + part * kStoreRows, (int)b, prm.out_mode == OUT_C64_ACCUM);
-                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
+                        // (an empty group keeps the group <-> ring-slot correspondence when nothing was stored)
+                        if (issuer) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        if (++ring == kStoreRing) ring = 0;
                     }
                     continue;
                 }
@@ -561,7 +571,7 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     prm.m_tiles = (int)ceil_div(fold ? B * Mm : Mm, kTileM);
     prm.tasks = B * prm.m_tiles;
     prm.n_tiles = (int)ceil_div(Nn, kTileN);
-    const size_t smem = (size_t)kStagesB * kStageBytes + 2 * kStoreBytes + sizeof(Barriers) + 1024;
+    const size_t smem = (size_t)kStagesB * kStageBytes + 2 * kStoreRing * kStoreBytes + sizeof(Barriers) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         SFA_CUDA_CHECK(cudaFuncSetAttribute(cgemm3x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -58,6 +58,43 @@ __global__ void norm_of_columns_kernel(long long M, long long N, const double2* 
     }
 }
 
+// Beam power map: P[r] = mean_t |q[r][t]|^2 for the R = F*L rows of a beam tensor [F, L, T] with row
+// pitch ld (the quantity the reference's examples plot, db(q) over look direction and frequency, and
+// the small collective of the multi-GPU path: [F, L] float32 instead of [F, L, T] complex64).
+// HBM-read-bound: 8 B in per beam output.  One warp per row, 16-byte loads when the row is aligned.
+__global__ void __launch_bounds__(256)
+power_map_kernel(long long R, long long T, long long ld, const float2* __restrict__ q, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float inv = 1.0f / (float)T;
+    for (long long r = warp; r < R; r += nwarps) {
+        const float2* row = q + r * ld;
+        float a0 = 0.f, a1 = 0.f;
+        if ((((size_t)row) & 15) == 0) {
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+            const long long T2 = T >> 1;
+            for (long long t = lane; t < T2; t += 32) {
+                const float4 v = __ldcs(row4 + t);           // streamed once
+                a0 = fmaf(v.x, v.x, fmaf(v.y, v.y, a0));
+                a1 = fmaf(v.z, v.z, fmaf(v.w, v.w, a1));
+            }
+            if ((T & 1) && lane == 0) {
+                const float2 v = row[T - 1];
+                a0 = fmaf(v.x, v.x, fmaf(v.y, v.y, a0));
+            }
+        } else {
+            for (long long t = lane; t < T; t += 32) {
+                const float2 v = __ldcs(row + t);
+                a0 = fmaf(v.x, v.x, fmaf(v.y, v.y, a0));
+            }
+        }
+        float acc = a0 + a1;
+        for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) out[r] = acc * inv;
+    }
+}
+
 // mutual coherence: max_{i != j} |<a_i, a_j>| / (|a_i| |a_j|); one CTA per column i
 __global__ void coherence_kernel(long long M, long long N, const double2* __restrict__ A,
                                  const double* __restrict__ norms, unsigned long long* __restrict__ best_bits) {
@@ -141,6 +178,18 @@ extern "C" int sfa_coherence_of_columns(int64_t M, int64_t N, const sfa_c128* A,
     SFA_LAUNCH_CHECK();
     coherence_kernel<<<(unsigned)N, 128, 0, st>>>(M, N, reinterpret_cast<const double2*>(A), norms,
                                                    reinterpret_cast<unsigned long long*>(result));
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+extern "C" int sfa_power_map(int64_t rows, int64_t T, int64_t ld, const sfa_c64* q, float* out, void* stream) {
+    if (rows < 0 || T <= 0 || ld < T) return SFA_ERR_INVALID;
+    if (rows == 0) return SFA_OK;
+    if (!q || !out) return SFA_ERR_INVALID;
+    long long blocks = sfa::ceil_div(rows, 8);
+    const long long cap = (long long)sfa::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    sfa::power_map_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rows, T, ld, reinterpret_cast<const float2*>(q), out);
     SFA_LAUNCH_CHECK();
     return SFA_OK;
 }

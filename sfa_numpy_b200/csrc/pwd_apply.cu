@@ -194,12 +194,14 @@ __global__ void d_to_float_kernel(const double2* __restrict__ d, long long n, fl
 static int launch_steer_build(const float2* G, const float2* d, int Cd, long long f0, int nf, long long LQ,
                               int hybrid, float* A, cudaStream_t st) {
     const dim3 grid((unsigned)ceil_div(LQ / 2, 128), (unsigned)ceil_div(nf, 8));
+    prof_aux_begin(st);
     if (Cd <= 16)
         steer_build_split_kernel<16><<<grid, 128, 0, st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
     else if (Cd <= 32)
         steer_build_split_kernel<32><<<grid, 128, 0, st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
     else
         steer_build_split_kernel<64><<<grid, 128, 0, st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
+    prof_aux_end(st);
     SFA_LAUNCH_CHECK();
     return SFA_OK;
 }
@@ -534,10 +536,12 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
     return SFA_OK;
 }
 
-// Form 1, several chunks: the (HBM-store-bound) steering-matrix build of chunk i+1 runs on a
-// side stream while the (tensor-bound) GEMM of chunk i runs on the caller's stream.  The GEMM
-// CTAs leave ~30 KB of shared memory and ~12 K registers per SM free, enough for the build CTAs
-// to be co-resident.
+// Form 1, several chunks: the (HBM-store-bound) steering-matrix build of chunk i+1 is issued on a
+// side stream as soon as its slab is free (GEMM i-1 done), the GEMM of chunk i on the caller's stream.
+// Measured with the launch timeline (sfa_prof_timeline, tools/prof_pwd.py): the block scheduler never
+// places a build CTA on an SM that hosts a persistent GEMM CTA, whatever the build CTA's size (tried
+// 32-128 threads x 62 registers, no shared memory, matching carve-out, stream priorities), so the
+// build runs in the ~48 us window between two GEMM launches, overlapping only their ramp-down/ramp-up.
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, built[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};

@@ -35,6 +35,8 @@ void count_launch();                 // bumps the library-wide kernel-launch cou
 bool prof_enabled();
 void prof_begin(cudaStream_t st);
 void prof_end(cudaStream_t st);
+void prof_aux_begin(cudaStream_t st);   // secondary spans (steering build), timeline only
+void prof_aux_end(cudaStream_t st);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

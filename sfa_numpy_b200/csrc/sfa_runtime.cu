@@ -45,7 +45,30 @@ void prof_end(cudaStream_t st) {
     g_prof_events.emplace_back(g_prof_open, b);
     g_prof_open = nullptr;
 }
+// secondary spans (kind 1: steering build) for the timeline tool
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_aux;
+static cudaEvent_t g_prof_aux_open = nullptr;
+void prof_aux_begin(cudaStream_t st) {
+    if (!g_prof) return;
+    cudaEvent_t a;
+    cudaEventCreate(&a);
+    cudaEventRecord(a, st);
+    g_prof_aux_open = a;
+}
+void prof_aux_end(cudaStream_t st) {
+    if (!g_prof || !g_prof_aux_open) return;
+    cudaEvent_t b;
+    cudaEventCreate(&b);
+    cudaEventRecord(b, st);
+    g_prof_aux.emplace_back(g_prof_aux_open, b);
+    g_prof_aux_open = nullptr;
+}
 static void prof_clear() {
+    for (auto& e : g_prof_aux) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    g_prof_aux.clear();
     for (auto& e : g_prof_events) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
@@ -76,6 +99,51 @@ int sfa_prof_read(double* total_ms, long long* count) {
     if (total_ms) *total_ms = tot;
     if (count) *count = (long long)sfa::g_prof_events.size();
     return SFA_OK;
+}
+
+// Elapsed time (ms) from the start of the first recorded launch to the end of the last one:
+// span - sum(durations) = idle gaps between the launches of the dominant kernel.
+int sfa_prof_span(double* span_ms) {
+    float ms = 0.f;
+    if (!sfa::g_prof_events.empty()) {
+        SFA_CUDA_CHECK(cudaEventSynchronize(sfa::g_prof_events.back().second));
+        SFA_CUDA_CHECK(cudaEventElapsedTime(&ms, sfa::g_prof_events.front().first, sfa::g_prof_events.back().second));
+    }
+    if (span_ms) *span_ms = ms;
+    return SFA_OK;
+}
+
+// Timeline of the recorded launches relative to the first GEMM start: rows of (kind, start_ms, end_ms),
+// kind 0 = tensor-core GEMM, 1 = steering build.  Returns the number of rows written.
+int sfa_prof_timeline(double* rows, int max_rows) {
+    if (sfa::g_prof_events.empty() || !rows) return 0;
+    cudaEvent_t t0 = sfa::g_prof_events.front().first;
+    int n = 0;
+    for (int kind = 0; kind < 2; ++kind) {
+        auto& v = kind == 0 ? sfa::g_prof_events : sfa::g_prof_aux;
+        for (auto& e : v) {
+            if (n >= max_rows) return n;
+            float a = 0.f, b = 0.f;
+            if (cudaEventSynchronize(e.second) != cudaSuccess) return n;
+            if (cudaEventElapsedTime(&a, t0, e.first) != cudaSuccess) {   // started before t0
+                cudaGetLastError();
+                float neg = 0.f;
+                cudaEventElapsedTime(&neg, e.first, t0);
+                a = -neg;
+            }
+            if (cudaEventElapsedTime(&b, t0, e.second) != cudaSuccess) {
+                cudaGetLastError();
+                float neg = 0.f;
+                cudaEventElapsedTime(&neg, e.second, t0);
+                b = -neg;
+            }
+            rows[3 * n] = kind;
+            rows[3 * n + 1] = a;
+            rows[3 * n + 2] = b;
+            ++n;
+        }
+    }
+    return n;
 }
 
 const char* sfa_strerror(int status) {

@@ -68,10 +68,15 @@ def all_gather_slabs(q_loc, F, group=None):
     return torch.cat([buf[r * big: r * big + sizes[r]] for r in range(world)], dim=0)
 
 
-def gather_power_map(q_loc, F, group=None):
+def gather_power_map(q_loc, F, group=None, reduce=None):
     """Frame-averaged beam power map mean_t |q|^2, [F, L] float32, gathered on every rank: the
-    cheap collective when only the map (not the beam signals) is needed downstream."""
-    p_loc = (q_loc.real.float() ** 2 + q_loc.imag.float() ** 2).mean(dim=-1)
+    cheap collective when only the map (not the beam signals) is needed downstream.  The local
+    reduction is `steering.power_map` (one CUDA kernel); `reduce` injects a replacement (the CPU
+    tests of the sharding logic do)."""
+    if reduce is None:
+        from .modal import steering
+        reduce = steering.power_map
+    p_loc = reduce(q_loc)
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return p_loc
     return all_gather_slabs(p_loc, F, group=group)

@@ -66,6 +66,23 @@ def _check_out(out, F, L, T, cdtype, dev):
     return out.stride(1)
 
 
+def power_map(q):
+    """Frame-averaged beam power ``mean_t |q[f, l, t]|^2`` as an [F, L] float32 tensor -- what the
+    reference's examples plot (``db(q)`` over look direction and frequency,
+    doc/examples/modal_beamforming_rigid_spherical_array.py:43-57) and the small collective of the
+    multi-GPU path.  `q` is a complex64 CUDA beam tensor as returned by `pwd` (row-padded views are
+    fine); one HBM-read-bound kernel, no intermediate tensors."""
+    if not (torch.is_tensor(q) and q.is_cuda and q.dtype == torch.complex64 and q.dim() == 3):
+        raise ValueError("power_map needs a complex64 CUDA tensor of shape (F, L, T)")
+    F, L, T = q.shape
+    ld = _check_out(q, F, L, T, torch.complex64, q.device)
+    out = torch.empty((F, L), dtype=torch.float32, device=q.device)
+    lib = _lib.load()
+    with torch.cuda.device(q.device):
+        _lib.check(lib.sfa_power_map(F * L, T, ld, _lib.ptr(q), _lib.ptr(out), _lib.stream_ptr(q.device)))
+    return out
+
+
 def pwd(Y_look, dn, Y_mic, p, precision=None, form="auto", out=None):
     """Apply the modal beamformer to microphone spectra.
 

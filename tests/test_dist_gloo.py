@@ -48,7 +48,10 @@ def _worker(rank, world, port, F, results):
         assert torch.equal(loc, loc2)
         gathered = sd.pwd_sharded(Y_look, dn, Y_mic, X, gather=True, compute=_torch_pwd)
         assert gathered.shape == full.shape and torch.allclose(gathered, full)
-        pm = sd.gather_power_map(loc.to(torch.complex64), F)
+        pm = sd.gather_power_map(loc.to(torch.complex64), F,
+                                 reduce=lambda q: (q.real.float() ** 2 + q.imag.float() ** 2).mean(dim=-1))
+        with pytest.raises(ValueError):                  # the product reduction is CUDA-only: no CPU fallback
+            sd.gather_power_map(loc.to(torch.complex64), F)
         assert pm.shape == (F, L)
         assert torch.allclose(pm, (full.abs() ** 2).mean(-1).float(), rtol=1e-4)
         results[rank] = True

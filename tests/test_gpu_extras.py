@@ -60,3 +60,23 @@ def test_forward_model_synthesis(golden):
     p = S.synthesize(A.cht_matrix(50, pol), Bn, A.cht_matrix(50, 1.23 * np.pi))
     ref = g["open_circular_p"]
     assert np.max(np.abs(cpu(p)[:, :, 0] - ref)) < 1e-11 * np.max(np.abs(ref))
+
+
+def test_power_map():
+    """mean_t |q|^2 of contiguous and row-padded beam tensors, odd and even T, against NumPy."""
+    import torch
+    import sfa_numpy_b200 as micarray
+    S = micarray.modal.steering
+    rng = np.random.default_rng(5)
+    for (F, L, T) in ((3, 17, 938), (2, 5, 7), (1, 64, 128), (4, 9, 1)):
+        qn = (rng.standard_normal((F, L, T)) + 1j * rng.standard_normal((F, L, T))).astype(np.complex64)
+        ref = np.mean(np.abs(qn.astype(np.complex128)) ** 2, axis=-1)
+        for padded in (False, True):
+            q = S.empty_beams(F, L, T, torch.complex64, torch.device("cuda")) if padded else \
+                torch.empty((F, L, T), dtype=torch.complex64, device="cuda")
+            q.copy_(torch.from_numpy(qn))
+            pm = S.power_map(q).cpu().numpy()
+            assert pm.shape == (F, L) and pm.dtype == np.float32
+            assert np.max(np.abs(pm - ref) / ref) < 2e-6
+    with pytest.raises(ValueError):
+        S.power_map(torch.zeros((2, 2, 2), dtype=torch.complex64))

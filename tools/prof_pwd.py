@@ -36,6 +36,14 @@ e1.record()
 torch.cuda.synchronize()
 tot, cnt = ctypes.c_double(), ctypes.c_longlong()
 lib.sfa_prof_read(ctypes.byref(tot), ctypes.byref(cnt))
+span = ctypes.c_double()
+lib.sfa_prof_span(ctypes.byref(span))
+if os.environ.get("SFA_TIMELINE"):
+    buf = (ctypes.c_double * (3 * 256))()
+    n = lib.sfa_prof_timeline(buf, 256)
+    rows = sorted((buf[3 * i + 1], buf[3 * i + 2], int(buf[3 * i])) for i in range(n))
+    for a, b, k in rows:
+        print("    %-5s %8.3f -> %8.3f ms  (%.3f)" % ("gemm" if k == 0 else "build", a, b, b - a))
 lib.sfa_prof_enable(0)
-print("  gemm kernels: %d launches, %.3f ms total" % (cnt.value, tot.value))
+print("  gemm kernels: %d launches, %.3f ms total, first start -> last end %.3f ms" % (cnt.value, tot.value, span.value))
 print(PREC, "F=%d: %.3f ms -> %.3e outputs/s" % (F, e0.elapsed_time(e1), F * L * T / e0.elapsed_time(e1) * 1e3))
