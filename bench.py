@@ -31,6 +31,8 @@ if os.environ.get("RANK", "0") == "0":
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_v] = str(os.cpu_count() or 1)
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner off stdout (one JSON line)
+
 import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -186,6 +186,78 @@ steer_build_split_kernel(const float2* __restrict__ G, const float2* __restrict_
     }
 }
 
+// Faster variant for few groups (spherical arrays up to order 15: Cd = N + 1 <= 16).  The kernel is as
+// much FP32-issue-bound as store-bound (36 FMAs per 16 bytes), so:
+//  * E adjacent entries per thread (E = 4: every store is 16 bytes per lane, 512 bytes per warp);
+//  * the diagonal of the CTA's bins sits in shared memory, pre-duplicated as (re, re, im, im) so that
+//    one 16-byte broadcast load feeds two packed FP32x2 FMAs (fma.rn.f32x2) per entry and group:
+//    P += re(d) * (g.re, g.im),  Q += im(d) * (g.re, g.im),  A = (P.x - Q.y, P.y + Q.x);
+//  * G is read once per 16-64 bins instead of once per 8.
+constexpr int kBuildMaxBins = 64;
+template <int NG, int E>
+__global__ void __launch_bounds__(128)
+steer_build_fast_kernel(const float2* __restrict__ G, const float2* __restrict__ d, int Cd, int nf, int bins_per_cta,
+                        long long LQ, int hybrid, float* __restrict__ A) {
+    __shared__ float4 sd[kBuildMaxBins * NG];
+    const int fa = (int)blockIdx.y * bins_per_cta;
+    const int fb = (fa + bins_per_cta < nf) ? fa + bins_per_cta : nf;
+    for (int i = threadIdx.x; i < (fb - fa) * NG; i += blockDim.x) {
+        const int f = i / NG, c = i - f * NG;
+        const float2 v = (c < Cd) ? __ldg(d + (long long)(fa + f) * Cd + c) : make_float2(0.f, 0.f);
+        sd[i] = make_float4(v.x, v.x, v.y, v.y);
+    }
+    __syncthreads();
+    const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * E;
+    if (e >= LQ) return;
+    float2 g[NG][E];
+#pragma unroll
+    for (int c = 0; c < NG; ++c) {
+#pragma unroll
+        for (int j = 0; j < E; j += 2) {
+            const float4 v = (c < Cd) ? __ldg(reinterpret_cast<const float4*>(G + (long long)c * LQ + e + j))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            g[c][j] = make_float2(v.x, v.y);
+            g[c][j + 1] = make_float2(v.z, v.w);
+        }
+    }
+    float* o = A + (long long)fa * 4 * LQ + e;
+    for (int f = 0; f < fb - fa; ++f) {
+        float2 P[E], Qa[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) P[j] = Qa[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < NG; ++c) {
+            const float4 dd = sd[f * NG + c];                  // same address for the whole warp: broadcast
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                P[j] = __ffma2_rn(make_float2(dd.x, dd.y), g[c][j], P[j]);
+                Qa[j] = __ffma2_rn(make_float2(dd.z, dd.w), g[c][j], Qa[j]);
+            }
+        }
+        float hr[E], hi[E], xr[E], xi[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const float ar = P[j].x - Qa[j].y, ai = P[j].y + Qa[j].x;
+            hr[j] = __uint_as_float(tf32_rna(ar));
+            hi[j] = __uint_as_float(tf32_rna(ai));
+            xr[j] = hybrid ? pack_bf16_lo_hi(hr[j], ar - hr[j]) : ar - hr[j];
+            xi[j] = hybrid ? pack_bf16_lo_hi(hi[j], ai - hi[j]) : ai - hi[j];
+        }
+        if (E == 4) {
+            __stcs(reinterpret_cast<float4*>(o), make_float4(hr[0], hr[1], hr[2], hr[3]));
+            __stcs(reinterpret_cast<float4*>(o + LQ), make_float4(hi[0], hi[1], hi[2], hi[3]));
+            __stcs(reinterpret_cast<float4*>(o + 2 * LQ), make_float4(xr[0], xr[1], xr[2], xr[3]));
+            __stcs(reinterpret_cast<float4*>(o + 3 * LQ), make_float4(xi[0], xi[1], xi[2], xi[3]));
+        } else {
+            __stcs(reinterpret_cast<float2*>(o), make_float2(hr[0], hr[1]));
+            __stcs(reinterpret_cast<float2*>(o + LQ), make_float2(hi[0], hi[1]));
+            __stcs(reinterpret_cast<float2*>(o + 2 * LQ), make_float2(xr[0], xr[1]));
+            __stcs(reinterpret_cast<float2*>(o + 3 * LQ), make_float2(xi[0], xi[1]));
+        }
+        o += 4 * LQ;
+    }
+}
+
 __global__ void d_to_float_kernel(const double2* __restrict__ d, long long n, float2* __restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = make_float2((float)d[i].x, (float)d[i].y);
@@ -195,7 +267,21 @@ static int launch_steer_build(const float2* G, const float2* d, int Cd, long lon
                               int hybrid, float* A, cudaStream_t st) {
     const dim3 grid((unsigned)ceil_div(LQ / 2, 128), (unsigned)ceil_div(nf, 8));
     prof_aux_begin(st);
-    if (Cd <= 16)
+    if (Cd <= 16 && !getenv("SFA_OLD_BUILD")) {
+        // ~8 CTAs per SM in flight; G is re-read once per `bpc` bins
+        const int E = Cd <= 9 ? 4 : 2;
+        const long long gx = ceil_div(LQ / E, 128);
+        long long gy = ceil_div((long long)sm_count() * 8, gx);
+        int bpc = (int)ceil_div(nf, gy < 1 ? 1 : gy);
+        if (bpc < 8) bpc = nf < 8 ? nf : 8;
+        if (bpc > kBuildMaxBins) bpc = kBuildMaxBins;
+        const dim3 fgrid((unsigned)gx, (unsigned)ceil_div(nf, bpc));
+        const float2* dd = d + f0 * Cd;
+        if (Cd <= 9)
+            steer_build_fast_kernel<9, 4><<<fgrid, 128, 0, st>>>(G, dd, Cd, nf, bpc, LQ, hybrid, A);
+        else
+            steer_build_fast_kernel<16, 2><<<fgrid, 128, 0, st>>>(G, dd, Cd, nf, bpc, LQ, hybrid, A);
+    } else if (Cd <= 16)
         steer_build_split_kernel<16><<<grid, 128, 0, st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
     else if (Cd <= 32)
         steer_build_split_kernel<32><<<grid, 128, 0, st>>>(G, d, Cd, Cd, f0, nf, LQ, hybrid, A);
