@@ -204,6 +204,59 @@ def cpu_baseline(O, cfg, azi, colat, w, azl, col, k):
             "stage3_outputs_per_s": outputs / best, "stage12_s": t_stage12}
 
 
+def tensor_bound_configs(torch, micarray, O, dev, precision):
+    """Stage 3 of the two tensor-bound BASELINE configs (cfg 4: N=16, 578 mics; cfg 5: N=32, 1089 mics) at
+    full size -- the in-kernel K-loop GEMM (cgemm3x_kloop_sm100.cu) -- next to a cuBLAS TF32 GEMM timed
+    on the same device.  `frac` = algorithmic real flops * passes / time / TF32 peak, passes = 2 (hybrid:
+    one tf32 pass + one bf16 pass of the same duration) or 3 (3xTF32)."""
+    A, R, S = micarray.modal.angular, micarray.modal.radial, micarray.modal.steering
+    a = torch.randn((8192, 8192), device=dev)
+    b = torch.randn((8192, 8192), device=dev)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    best = 1e9
+    for _ in range(8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    torch.backends.cuda.matmul.allow_tf32 = old
+    tf32_peak = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+    del a, b
+    passes = 2 if precision == "c64_fast" else 3
+    rows = []
+    for name, N, grid, F, L, T, r, setup in (("cfg4", 16, "gauss", 1024, 2562, 64, 0.1, "card"),
+                                             ("cfg5", 32, 1089, 4096, 16384, 32, 0.2, "rigid")):
+        az, co, w = O.grid_gauss(N) if grid == "gauss" else O.fibonacci_grid(grid)
+        azl, col, _ = O.fibonacci_grid(L)
+        Y_p, Y_q = A.sht_matrix(N, az, co, w), A.sht_matrix(N, azl, col)
+        _, dn, _ = R.radial_filters(N, O.wavenumbers(F) + 0.1, r, setup, 100.0, "Tikh")
+        Q, M = Y_p.shape
+        X = torch.randn((F, Q, T), dtype=torch.complex64, device=dev)
+        plan = S.PwdPlan(Y_q, dn, Y_p, T, precision=precision)
+        out = S.empty_beams(F, L, T, torch.complex64, dev)
+        for _ in range(2):
+            plan(X, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            plan(X, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        flops = 8.0 * F * T * M * (Q + L)
+        rows.append({"config": "%s: N=%d, %d mics, F=%d, L=%d, T=%d (factored form, K-loop GEMM)" % (name, N, Q, F, L, T),
+                     "ms": ms, "outputs_per_s": F * L * T / (ms * 1e-3), "alg_tflops": flops / (ms * 1e-3) / 1e12,
+                     "tensor_passes": passes, "cublas_tf32_tflops": tf32_peak,
+                     "frac_of_tf32_peak": flops * passes / (ms * 1e-3) / 1e12 / tf32_peak})
+        del X, out, plan, Y_p, Y_q, dn
+        torch.cuda.empty_cache()
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,6 +267,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stage12", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--precision", default="c64_fast", choices=["c64", "c64_fast"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -306,13 +360,13 @@ def main():
     n_prof = max(2, min(args.steps, 5))
     launches_per_step = cnt.value / n_prof
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (74 bins) from the committed ncu
-    # capture profiles/r1_f_cgemm3x_hybrid_cluster_tmastore.txt; bench.py itself never runs under ncu.
-    NCU_TRAFFIC_74_BINS = 1.380845e9 + 0.292279e9
+    # capture profiles/r1_i_cgemm3x_hybrid_2stage_ring2.txt; bench.py itself never runs under ncu.
+    NCU_TRAFFIC_74_BINS = 1.377538e9 + 0.242853e9
     roofline = {"kernel": "cgemm3x_kernel<%s> (tcgen05 steering GEMM)" % ("hybrid" if args.precision == "c64_fast" else "3xTF32"), "bound": "hbm",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"],
                 "traffic": NCU_TRAFFIC_74_BINS if args.precision == "c64_fast" else None,
-                "traffic_source": "ncu --set full, one 74-bin launch (profiles/r1_f_cgemm3x_hybrid_cluster_tmastore.txt)",
+                "traffic_source": "ncu --set full, one 74-bin launch (profiles/r1_i_cgemm3x_hybrid_2stage_ring2.txt)",
                 "alg_bytes_per_launch": alg_bytes / launches_per_step if launches_per_step else None,
                 "kernel_ms_per_launch": gemm_ms_per_step / launches_per_step if launches_per_step else None,
                 "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
@@ -417,9 +471,16 @@ def main():
                                 for k2, v in r.items()} for r in rows]
         except Exception as e:
             line["stage12"] = {"error": repr(e)}
+    if rank == 0 and not args.no_other_configs:
+        try:
+            torch.cuda.empty_cache()
+            line["tensor_bound_configs"] = tensor_bound_configs(torch, micarray, O, dev, args.precision)
+        except Exception as e:
+            line["tensor_bound_configs"] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()                 # rank 0 may still be timing its CPU / single-GPU extras
         dist.destroy_process_group()
 
 
