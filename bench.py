@@ -31,7 +31,14 @@ if os.environ.get("RANK", "0") == "0":
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_v] = str(os.cpu_count() or 1)
 
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner off stdout (one JSON line)
+# stdout carries exactly ONE JSON line: everything else that writes to file descriptor 1 (NCCL prints its
+# version banner there) is sent to stderr; the line itself goes to the saved descriptor.
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
 
 import numpy as np  # noqa: E402
 
@@ -122,6 +129,20 @@ def use_all_host_threads():
         return int(os.environ.get("OMP_NUM_THREADS", n))
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs next to GPU `index` (NVML's ideal affinity), so that the pinned host
+    buffers of the e2e path are first-touched on the GPU's own NUMA node.  Returns the previous CPU set."""
+    try:
+        import pynvml
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return prev
+    except Exception:
+        return None
+
+
 def make_inputs(O, cfg, rank):
     azi, colat, w = O.grid_equal_angle(3)                 # 64 microphones
     azl, col, _ = O.fibonacci_grid(cfg["L"])
@@ -173,7 +194,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "outputs/s", "cores": threads, "kind": "port",
                              "sample": sample},
             "e2e": {"value": val, "unit": "outputs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline(O, cfg, azi, colat, w, azl, col, k):
@@ -422,6 +443,7 @@ def main():
     # ---- e2e through the host-buffer C ABI: every rank pushes its own batch through its own PCIe link ----
     if not args.no_e2e:
         host, err = None, None
+        prev_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
         try:
             torch.cuda.synchronize()
             Yq_h = A.sht_matrix(N, d_azl, d_coll).cpu().numpy()
@@ -459,6 +481,8 @@ def main():
             line["e2e"] = {"value": None, "unit": "outputs/s", "error": err or "another rank failed to set up"}
         if host is not None:
             host.close()
+        if prev_cpus:
+            os.sched_setaffinity(0, prev_cpus)           # the CPU baseline below uses every core again
     if rank == 0 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(O, cfg, azi, colat, w, azl, col, k)
     if rank == 0 and not args.no_stage12:
@@ -478,7 +502,7 @@ def main():
         except Exception as e:
             line["tensor_bound_configs"] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()                 # rank 0 may still be timing its CPU / single-GPU extras
         dist.destroy_process_group()
