@@ -61,6 +61,13 @@ def test_cht(mic, golden):
     assert_close(cpu(A.cht_matrix(0, 1.25)), g["c0_Psi"], **TOL, name="c0")
     pol = np.linspace(-20, 20, 1000)
     assert_close(cpu(A.cht_matrix(30, pol)), O.cht_matrix(30, pol), **TOL, name="c30")
+    # many rows: the shared-memory row-block kernel (recurrence in n), ragged last block, weights
+    rng = np.random.default_rng(7)
+    for N, Q in ((16, 5000), (1, 4097), (40, 4100), (100, 4096)):
+        pol = rng.uniform(-4 * np.pi, 4 * np.pi, Q)
+        w = rng.uniform(0.1, 2.0, Q)
+        assert_close(cpu(A.cht_matrix(N, pol, w)), O.cht_matrix(N, pol, w), **TOL, name="rows N=%d" % N)
+    assert_close(cpu(A.cht_matrix(16, pol[:4096])), O.cht_matrix(16, pol[:4096]), **TOL, name="rows no weights")
 
 
 @pytest.mark.parametrize("setup", O.SETUPS)
