@@ -215,7 +215,9 @@ struct sph_yn_iter {
 // Y_1 = -(2/(pi x)) J_0 + (2/pi)(ln(x/2)+gamma-1) J_1
 //       - (2/pi) sum_{k>=1} (-1)^k (2k+1)/(k(k+1)) J_{2k+1}                      (A&S 9.1.88, n=1)
 // ---------------------------------------------------------------------------
-SFA_HD void cyl_jn_array(int nmax, double x, dvec J, double* Y0, double* Y1) {
+// `rk_tab` (optional): table of 1/k for k < rk_len, so the Miller loop carries no FP64 division.
+SFA_HD void cyl_jn_array(int nmax, double x, dvec J, double* Y0, double* Y1, const double* rk_tab = nullptr,
+                         int rk_len = 0) {
     if (x == 0.0) {
         J[0] = 1.0;
         for (int n = 1; n <= nmax; ++n) J[n] = 0.0;
@@ -234,7 +236,7 @@ SFA_HD void cyl_jn_array(int nmax, double x, dvec J, double* Y0, double* Y1) {
     double sum_y1 = 0.0;                 // sum (-1)^k (1/k + 1/(k+1)) f_{2k+1}
     double rk1 = 0.0;                    // 1/(k+1)
     for (int k = n >> 1; k >= 1; --k) {
-        const double rk = 1.0 / (double)k;
+        const double rk = (k < rk_len) ? rk_tab[k] : 1.0 / (double)k;
         const double sg = (k & 1) ? -1.0 : 1.0;
         sum_y1 += sg * fo * (rk + rk1);
         sum_even += fe;
@@ -381,10 +383,19 @@ SFA_HD void sph_radial_row(int N, double k, double r, double rs, int setup, int 
                 } else {
                     yd = yx.ym1 - (n + 1) * ix * yn;
                 }
-                const c128 hn = mk(jn, -yn);
-                const c128 hd = mk(jd, -yd);
-                const c128 q = cdiv(mk(jd, 0.0), hd);
-                b = csub(mk(jn, 0.0), cmul(q, hn));
+                // j_n - (j_n'/h_n') h_n = -i W[j_n, y_n] / h_n' = -i / (x^2 h_n'), h = j - i y (Wronskian
+                // 1/x^2): one real division instead of a complex one, and no cancellation.  Outside the
+                // range where |h_n'|^2 is safe the reference's expression is evaluated literally.
+                const double mag = fmax(fabs(jd), fabs(yd));
+                if (mag > 1e-140 && mag < 1e140) {
+                    const double inv = 1.0 / ((x * x) * (jd * jd + yd * yd));
+                    b = mk(yd * inv, -jd * inv);
+                } else {
+                    const c128 hn = mk(jn, -yn);
+                    const c128 hd = mk(jd, -yd);
+                    const c128 q = cdiv(mk(jd, 0.0), hd);
+                    b = csub(mk(jn, 0.0), cmul(q, hn));
+                }
             }
         }
         if (need_y) yx.step();
@@ -410,11 +421,11 @@ SFA_HD void sph_radial_row(int N, double k, double r, double rs, int setup, int 
 
 template <class Out>
 SFA_HD void circ_radial_row(int N, double k, double r, double rs, int setup, int scale,
-                            dvec jx, dvec js, Out out) {
+                            dvec jx, dvec js, Out out, const double* rk_tab = nullptr, int rk_len = 0) {
     const double x = k * r;
     const int top = N + 1;               // J_N' = (J_{N-1} - J_{N+1})/2
     double Y0 = 0.0, Y1 = 0.0;
-    cyl_jn_array(top, x, jx, &Y0, &Y1);
+    cyl_jn_array(top, x, jx, &Y0, &Y1, rk_tab, rk_len);
     const double ix2 = (x != 0.0) ? 2.0 / x : 0.0;
     // forward recurrence window for Y: (ym1, y, yp1) = (Y_{n-1}, Y_n, Y_{n+1})
     double ym1 = -Y1, y = Y0, yp1 = Y1;  // Y_{-1} = -Y_1
@@ -422,7 +433,7 @@ SFA_HD void circ_radial_row(int N, double k, double r, double rs, int setup, int
     double S0 = 0.0, S1 = 0.0;
     double sm1 = 0.0, s = 0.0;
     if (scale == 2) {
-        cyl_jn_array(top, xs, js, &S0, &S1);
+        cyl_jn_array(top, xs, js, &S0, &S1, rk_tab, rk_len);
         sm1 = -S1;
         s = S0;
     }
@@ -442,10 +453,17 @@ SFA_HD void circ_radial_row(int N, double k, double r, double rs, int setup, int
                 b = mk(Jn, 0.0);                             // radial.py:429-431
             } else {
                 const double Yd = 0.5 * (ym1 - yp1);
-                const c128 Hn = mk(Jn, -y);
-                const c128 Hd = mk(Jd, -Yd);
-                const c128 q = cdiv(mk(Jd, 0.0), Hd);
-                b = csub(mk(Jn, 0.0), cmul(q, Hn));
+                // J_n - (J_n'/H_n') H_n = -i W[J_n, Y_n] / H_n' = -2i / (pi x H_n')  (Wronskian 2/(pi x))
+                const double mag = fmax(fabs(Jd), fabs(Yd));
+                if (mag > 1e-140 && mag < 1e140) {
+                    const double inv = 0.63661977236758134308 / (x * (Jd * Jd + Yd * Yd));
+                    b = mk(Yd * inv, -Jd * inv);
+                } else {
+                    const c128 Hn = mk(Jn, -y);
+                    const c128 Hd = mk(Jd, -Yd);
+                    const c128 q = cdiv(mk(Jd, 0.0), Hd);
+                    b = csub(mk(Jn, 0.0), cmul(q, Hn));
+                }
             }
         }
         if (setup == SETUP_RIGID && x != 0.0) {

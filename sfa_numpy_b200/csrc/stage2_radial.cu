@@ -20,11 +20,15 @@ namespace sfa {
 
 constexpr double kZeroThreshold = 1e-300;    // radial.py:198
 constexpr int kRadialThreads = 128;
+constexpr int kRkTable = 256;
 constexpr long long kWorklistCap = 1 << 20;  // zero entries that can be repaired per call
 
 struct TileOut {
     double2* row;
-    __device__ __forceinline__ void operator()(int c, c128 v) const { row[c] = make_double2(v.re, v.im); }
+    int ncols;      // columns kept in the tile (circle: only the orders n >= 0, the mirror is rebuilt on the way out)
+    __device__ __forceinline__ void operator()(int c, c128 v) const {
+        if (c < ncols) row[c] = make_double2(v.re, v.im);
+    }
 };
 
 __device__ __forceinline__ bool is_zero_entry(double2 v) { return cabs_less(mk(v.x, v.y), kZeroThreshold); }
@@ -40,11 +44,21 @@ radial_filter_kernel(int N, long long F, const double* __restrict__ k, double r,
                      long long* __restrict__ worklist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int C = FAMILY ? 2 * N + 1 : N + 1;
-    const int Cp = C | 1;                                   // odd row pitch: conflict-free 16 B rows
+    // Circle: column C-n is (-1)^n column n for the bare weights and EQUAL to column n once the i^n /
+    // H_n factors are applied ((-1)^n i^-n = i^n, H_-n = (-1)^n H_n; radial.py:345-348, 388-390, 440), so
+    // the tile keeps the N+1 non-negative orders only: half the shared memory per wavenumber (twice the
+    // resident warps for these latency-bound FP64 recurrences) and one regularised inverse per pair.
+    const int Ct = N + 1;                                   // tile columns
+    const int Cp = Ct | 1;                                  // odd row pitch: conflict-free 16 B rows
     const int T = blockDim.x;
     double2* tile = reinterpret_cast<double2*>(smem_raw);   // [T][Cp]
     double* scratch = reinterpret_cast<double*>(tile + (size_t)T * Cp);   // 1 or 2 arrays [(N+3)][T]
     const int tid = threadIdx.x;
+    __shared__ double rk_tab[kRkTable];                     // 1/k for the cylinder Miller loop
+    if (FAMILY == 1) {
+        for (int i = tid; i < kRkTable; i += T) rk_tab[i] = i ? 1.0 / (double)i : 0.0;
+        __syncthreads();
+    }
     const long long nblk = (F + T - 1) / T;
     for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         const long long f0 = blk * T;
@@ -52,31 +66,37 @@ radial_filter_kernel(int N, long long F, const double* __restrict__ k, double r,
         if (f < F) {
             dvec jx{scratch + tid, T};
             dvec js{scratch + (size_t)(N + 3) * T + tid, T};
-            TileOut out{tile + (size_t)tid * Cp};
+            TileOut out{tile + (size_t)tid * Cp, Ct};
             if (FAMILY == 0) sph_radial_row(N, k[f], r, rs, SETUP, SCALE, jx, js, out);
-            else circ_radial_row(N, k[f], r, rs, SETUP, SCALE, jx, js, out);
+            else circ_radial_row(N, k[f], r, rs, SETUP, SCALE, jx, js, out, rk_tab, kRkTable);
         }
         __syncthreads();
         const int rows = (int)((F - f0 < T) ? (F - f0) : T);
-        const int total = rows * C;
+        const int total = rows * Ct;
         int local_zero = 0;
-        // (row, col) of element e = tid, tid + T, ... tracked incrementally (no division per element)
-        int rr = tid / C, cc = tid - rr * C;
-        const int drr = T / C, dcc = T - drr * C;
+        // (row, col) of tile element e = tid, tid + T, ... tracked incrementally (no division per element)
+        int rr = tid / Ct, cc = tid - rr * Ct;
+        const int drr = T / Ct, dcc = T - drr * Ct;
         for (int e = tid; e < total; e += T, rr += drr, cc += dcc) {
-            if (cc >= C) {
-                cc -= C;
+            if (cc >= Ct) {
+                cc -= Ct;
                 ++rr;
             }
             const double2 b = tile[(size_t)rr * Cp + cc];
-            const long long g = f0 * C + e;
+            const long long g = (f0 + rr) * C + cc;
+            const bool mirror = FAMILY == 1 && cc > 0;          // also emit column C - n
+            const long long gm = (f0 + rr) * C + (C - cc);
+            const double sgn = (SCALE == 0 && (cc & 1)) ? -1.0 : 1.0;
             bn[g] = b;
+            if (mirror) bn[gm] = make_double2(sgn * b.x, sgn * b.y);
             if (is_zero_entry(b)) {
-                ++local_zero;
+                local_zero += mirror ? 2 : 1;
                 if (want_zero_list) {
-                    const int slot = atomicAdd(&status[3], 1);
-                    if (slot < kWorklistCap) worklist[slot] = g;
-                    else status[2] = 1;
+                    const int slot = atomicAdd(&status[3], mirror ? 2 : 1);
+                    if (slot + (mirror ? 1 : 0) < kWorklistCap) {
+                        worklist[slot] = g;
+                        if (mirror) worklist[slot + 1] = gm;
+                    } else status[2] = 1;
                 }
             }
             if (method >= 0) {
@@ -86,6 +106,11 @@ radial_filter_kernel(int N, long long F, const double* __restrict__ k, double r,
                 dn[g] = make_double2(d.re, d.im);
                 if (hn_real) hn_real[g] = h;
                 else hn_cplx[g] = make_double2(h, 0.0);
+                if (mirror) {                                    // 1/(-b) = -(1/b), same |.| and h
+                    dn[gm] = make_double2(sgn * d.re, sgn * d.im);
+                    if (hn_real) hn_real[gm] = h;
+                    else hn_cplx[gm] = make_double2(h, 0.0);
+                }
             }
         }
         if (local_zero) atomicAdd(&status[0], local_zero);
@@ -266,7 +291,8 @@ extern "C" int sfa_radial_filter(int kind, int N, int64_t F, const double* k, do
     const int family = kind >= SFA_CIRC_WEIGHTS;
     const int scale = family ? kind - SFA_CIRC_WEIGHTS : kind;
     const int C = family ? 2 * N + 1 : N + 1;
-    const int Cp = C | 1;
+    const int Cp = (N + 1) | 1;                 // tile columns: the non-negative orders (see the kernel)
+    (void)C;
     // rows per CTA: as many as fit in shared memory (large orders, e.g. the examples' N = 50 circle
     // with 101 columns, run with narrower CTAs)
     int T = kRadialThreads;
