@@ -101,8 +101,10 @@ __global__ void expand_diag_kernel(const double2* __restrict__ d, long long F, i
 }
 
 // G[g][l*Qp + q] = sum_{m in group g} Y_L[l,m] * conj(Y_Q[q,m])   (FP64 accumulate)
+// YQt = conj(Y_Q)^T, [M][Q]: consecutive lanes (consecutive q) read consecutive 16-byte values; with
+// Y_Q[q*M + m] every load touched 32 lines and the kernel was L1-wavefront-bound (42 us on cfg 3).
 template <class T2>
-__global__ void group_products_kernel(const double2* __restrict__ YL, const double2* __restrict__ YQ, long long L,
+__global__ void group_products_kernel(const double2* __restrict__ YL, const double2* __restrict__ YQt, long long L,
                                       long long Q, long long Qp, int M, int G, int per_order,
                                       T2* __restrict__ out) {
     const long long total = L * Qp;
@@ -116,9 +118,9 @@ __global__ void group_products_kernel(const double2* __restrict__ YL, const doub
                 const int m1 = per_order ? (g + 1) * (g + 1) : g + 1;
                 for (int m = m0; m < m1 && m < M; ++m) {
                     const double2 a = YL[l * M + m];
-                    const double2 b = YQ[q * M + m];
-                    sr += a.x * b.x + a.y * b.y;       // a * conj(b)
-                    si += a.y * b.x - a.x * b.y;
+                    const double2 b = YQt[(long long)m * Q + q];
+                    sr += a.x * b.x - a.y * b.y;       // a * conj(Y_Q[q,m])
+                    si += a.y * b.x + a.x * b.y;
                 }
             }
             T2 o;
@@ -418,7 +420,7 @@ struct Plan {
     long long Qp, Mp, Tld, Old; // padded k extents / leading dims (Z rows, out rows)
     int ngroups;
     long long fc;               // bins per chunk
-    size_t off_G, off_A, off_dF, off_P1, off_P2, off_dcols, off_Z, off_scratch, scratch_bytes, total, a_slab;
+    size_t off_YQt, off_G, off_A, off_dF, off_P1, off_P2, off_dcols, off_Z, off_scratch, scratch_bytes, total, a_slab;
 };
 
 static inline bool is_c64(const sfa_pwd_shape* s) {
@@ -484,7 +486,10 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
     p->off_G = p->off_A = p->off_dF = p->off_P1 = p->off_P2 = p->off_dcols = p->off_Z = p->a_slab = 0;
     p->off_scratch = p->scratch_bytes = 0;
     const size_t esz = c64 ? 8 : 16;
+    p->off_YQt = 0;
     if (form == 1) {
+        p->off_YQt = off;                                     // conj(Y_Q)^T for the group products
+        off += align_up((size_t)s->M * s->Q * 16);
         p->off_G = off;
         off += align_up((size_t)s->Cd * s->L * p->Qp * esz);
         p->off_A = off;                                       // two slabs: build(i+1) overlaps gemm(i)
@@ -540,11 +545,14 @@ static int pwd_prepare(const sfa_pwd_shape* s, const Plan& p, const double2* yl,
     const bool c64 = is_c64(s);
     const long long LQ = L * p.Qp;
     if (p.form == 1) {
+        double2* yqt = reinterpret_cast<double2*>(w + p.off_YQt);
+        conj_transpose_kernel<<<grid1d(Q * M), 256, 0, st>>>(yq, Q, M, yqt);
+        SFA_LAUNCH_CHECK();
         if (c64)
-            group_products_kernel<float2><<<grid1d(LQ), 256, 0, st>>>(yl, yq, L, Q, p.Qp, M, Cd, s->d_is_per_order,
+            group_products_kernel<float2><<<grid1d(LQ), 256, 0, st>>>(yl, yqt, L, Q, p.Qp, M, Cd, s->d_is_per_order,
                                                                      reinterpret_cast<float2*>(w + p.off_G));
         else
-            group_products_kernel<double2><<<grid1d(LQ), 256, 0, st>>>(yl, yq, L, Q, p.Qp, M, Cd, s->d_is_per_order,
+            group_products_kernel<double2><<<grid1d(LQ), 256, 0, st>>>(yl, yqt, L, Q, p.Qp, M, Cd, s->d_is_per_order,
                                                                       reinterpret_cast<double2*>(w + p.off_G));
         SFA_LAUNCH_CHECK();
     } else if (c64) {

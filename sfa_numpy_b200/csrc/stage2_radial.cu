@@ -122,34 +122,34 @@ radial_filter_kernel(int N, long long F, const double* __restrict__ k, double r,
 // kr whose entry in the same column is non-zero (ties -> smaller kr, which is what
 // argmin over the kr-sorted rows gives, radial.py:200-206).  One warp per entry.
 // `order` maps sorted position -> row (NULL: rows are already sorted by kr).
-__global__ void find_replacement_kernel(long long F, int C, const double* __restrict__ kr,
-                                        const double2* __restrict__ A, int* __restrict__ status,
-                                        long long* __restrict__ worklist) {
+__global__ void __launch_bounds__(256)
+find_replacement_kernel(long long F, int C, const double* __restrict__ kr,
+                        const double2* __restrict__ A, int* __restrict__ status,
+                        long long* __restrict__ worklist) {
+    // One CTA per listed entry (the normal case is a handful of entries: the k = 0 row): 256 threads
+    // scan the F rows of the column, then a warp-shuffle + shared-memory argmin.
+    __shared__ double s_best[8], s_bestk[8];
+    __shared__ long long s_besti[8];
     const int nlist = min((long long)status[3], kWorklistCap);
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long e = warp; e < nlist; e += nwarps) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (long long e = blockIdx.x; e < nlist; e += gridDim.x) {
         const long long g = worklist[e];
         const long long i = g / C;
         const int j = (int)(g - i * C);
         const double ki = kr[i];
         double best = INFINITY, bestk = INFINITY;
         long long besti = -1;
-        for (long long l = lane; l < F; l += 32) {
+        for (long long l = threadIdx.x; l < F; l += blockDim.x) {
             if (is_zero_entry(A[l * C + j])) continue;
-            const double dist = fabs(kr[l] - ki);
             const double kl = kr[l];
+            const double dist = fabs(kl - ki);
             if (dist < best || (dist == best && (kl < bestk || (kl == bestk && l < besti)))) {
                 best = dist;
                 bestk = kl;
                 besti = l;
             }
         }
-        for (int off = 16; off; off >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-            const double ok = __shfl_xor_sync(0xffffffffu, bestk, off);
-            const long long oi = __shfl_xor_sync(0xffffffffu, besti, off);
+        auto merge = [&](double ob, double ok, long long oi) {
             const bool take = (oi >= 0) && (besti < 0 || ob < best ||
                               (ob == best && (ok < bestk || (ok == bestk && oi < besti))));
             if (take) {
@@ -157,11 +157,25 @@ __global__ void find_replacement_kernel(long long F, int C, const double* __rest
                 bestk = ok;
                 besti = oi;
             }
+        };
+        for (int off = 16; off; off >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const double ok = __shfl_xor_sync(0xffffffffu, bestk, off);
+            const long long oi = __shfl_xor_sync(0xffffffffu, besti, off);
+            merge(ob, ok, oi);
         }
         if (lane == 0) {
+            s_best[wib] = best;
+            s_bestk[wib] = bestk;
+            s_besti[wib] = besti;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) merge(s_best[w], s_bestk[w], s_besti[w]);
             if (besti < 0) status[1] = 1;
             worklist[kWorklistCap + e] = besti;
         }
+        __syncthreads();
     }
 }
 
