@@ -81,3 +81,29 @@ def test_product_never_imports_oracle():
                 assert "oracle" not in src.replace("oracle/", "oracle/") or f == "build.py" or \
                     "import oracle" not in src and "from oracle" not in src, f
                 assert "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_pwd_workspace_plan_without_gpu():
+    """sfa_pwd_work_bytes runs the planner (form selection, chunking, scratch of the K-loop kernel) on the
+    host: every BASELINE shape gets a finite, plausible workspace in each form it supports."""
+    from sfa_numpy_b200 import _lib
+    lib = _lib.load()
+    shapes = {  # F, L, Q, T, M, Cd, per_order
+        "cfg1": (512, 360, 100, 256, 25, 5, 1),
+        "cfg2": (1024, 360, 32, 256, 33, 33, 0),
+        "cfg3": (1024, 2562, 64, 938, 81, 9, 1),
+        "cfg4": (1024, 2562, 578, 64, 289, 17, 1),
+        "cfg5": (4096, 16384, 1089, 32, 1089, 33, 1),
+    }
+    for name, (F, L, Q, T, M, Cd, per) in shapes.items():
+        for prec in (0, 1, 2):
+            sizes = {}
+            for form in (0, 1, 2):
+                sh = _lib.PwdShape(F, L, Q, T, M, Cd, per, prec, form, 0)
+                sizes[form] = lib.sfa_pwd_work_bytes(sh)
+            assert 0 < sizes[0] < 8 << 30, (name, prec, sizes)          # auto: always plannable, a few GB at most
+            assert sizes[2] > 0, (name, prec)                            # factored form: always
+            assert sizes[0] in (sizes[1], sizes[2]), (name, prec, sizes)  # auto picks one of the two forms
+    # malformed shapes are rejected (0 bytes), not planned
+    assert lib.sfa_pwd_work_bytes(_lib.PwdShape(8, 4, 4, 4, 9, 4, 1, 0, 0, 0)) == 0      # Cd^2 != M
+    assert lib.sfa_pwd_work_bytes(_lib.PwdShape(8, 4, 4, 4, 9, 3, 1, 7, 0, 0)) == 0      # unknown precision

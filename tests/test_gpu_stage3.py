@@ -57,7 +57,9 @@ def test_cgemm3x_direct(mic):
     cases = [(1, 64, 128, 8), (2, 70, 200, 64), (3, 5, 33, 3), (1, 130, 129, 100), (2, 64, 256, 37),
              (1, 200, 1000, 64), (4, 17, 938, 9),
              # long inner dimension (in-kernel K loop when P is shared): folded bins, ragged n / k tails
-             (3, 200, 40, 289), (2, 300, 64, 1089), (5, 129, 33, 65), (7, 16, 32, 97), (1, 257, 300, 130)]
+             (3, 200, 40, 289), (2, 300, 64, 1089), (5, 129, 33, 65), (7, 16, 32, 97), (1, 257, 300, 130),
+             # single (partial) row tile; exactly one accumulation block (9 x 32) and one k beyond it; many blocks
+             (1, 40, 50, 100), (2, 64, 32, 288), (2, 64, 32, 289), (1, 130, 32, 2048)]
     for (B, Nn, Mm, K) in cases:
         for shared in (False, True):
             Pn = (rng.standard_normal((1 if shared else B, Nn, K)) + 1j * rng.standard_normal((1 if shared else B, Nn, K))).astype(np.complex64)
