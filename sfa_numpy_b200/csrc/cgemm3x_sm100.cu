@@ -30,16 +30,20 @@
 //   * UMMA N = 64 rows n of P per step.  P is always produced by this library
 //     (steering matrices, SH matrices), so it is stored pre-split and planar
 //     ([4 planes][n][k] fp32).  One elected thread streams it with TMA
-//     (cp.async.bulk.tensor, SWIZZLE_128B) into a 3-stage shared-memory ring in
-//     exactly the canonical K-major layout the UMMA descriptor reads.
+//     (cp.async.bulk.tensor, SWIZZLE_128B) into a 2-stage shared-memory ring in
+//     exactly the canonical K-major layout the UMMA descriptor reads; the two CTAs of a
+//     cluster (m-tiles 2j, 2j+1 of one batch) fetch half of the boxes each and multicast them.
 //   * One elected thread issues the tcgen05.mma.kind::tf32 stream:
 //     3 passes x 4 real products x K/8 k-steps per n-tile, accumulating into a
 //     double-buffered pair of TMEM accumulators (Re, Im: 64 columns each).
 //   * Eight epilogue warps read the accumulators with tcgen05.ld (lane = m, 32 columns
-//     per warp), release the accumulator at once and store complex64 directly: a warp
-//     writes 32 consecutive m of one row n = 256 contiguous bytes per store instruction,
-//     no shared-memory transpose.
+//     per warp), release the accumulator at once, stage 16-row pieces of the tile in a
+//     2-deep ring of 16 KB shared-memory buffers per column half and write them with TMA
+//     stores (reduce-add for split-K passes).  Rows that are not 16-byte aligned (odd ldo) and
+//     folded batches store complex64 directly from registers: a warp writes 32 consecutive m of
+//     one row n = 256 contiguous bytes per store instruction.
 // TMEM budget: 2 x (64 Re + 64 Im) accumulator columns + 256 operand columns = 512.
+// SMEM: 2 x 64 KB operand stages + 2 x 2 x 16 KB store staging.
 #include <cuda.h>
 #include <stdlib.h>
 #include "sfa_common.cuh"
