@@ -229,11 +229,13 @@ def test_pwd_host_path(mic):
     S = mic.modal.steering
     for T in (70, 138):                  # 138 > 128 and not a multiple of 32: row-padded device buffer + 2-D D2H copy
         _host_path_case(S, T)
+    _host_path_case(S, 40, N=8, grid=100)    # 100 channels, 81 modes: factored form through the K-loop kernel
 
 
-def _host_path_case(S, T):
-    N, Q, L, F = 4, 50, 200, 37
-    az, co, w = O.grid_gauss(N)
+def _host_path_case(S, T, N=4, grid=None):
+    L, F = 200, 37
+    az, co, w = O.grid_gauss(N) if grid is None else O.fibonacci_grid(grid)
+    Q = len(az)
     azl, col, _ = O.fibonacci_grid(L)
     Yp_ref, Yq_ref = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
     k = O.wavenumbers(F) + 0.5
