@@ -86,7 +86,6 @@ struct Params {
     int kchunks;
     int block_chunks, nblocks;    // accumulation blocks (chunks per block, blocks per task)
     float2* scratch;              // [grid][4 lane quarters][128 n][32 rows] running sum of the block partials
-    int prefetch;                 // loaders prefetch their next chunk into L2
 };
 
 struct __align__(8) Barriers {
@@ -314,12 +313,6 @@ cgemm3x_kloop_kernel(const __grid_constant__ CUtensorMap p_map, const Params prm
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     v[j] = (m_ok && k0 + j < prm.K) ? __ldg(src + (long long)(k0 + j) * prm.ldR) : make_float2(0.f, 0.f);
-                if (prm.prefetch && m_ok && kc + 2 < kchunks) {  // this set's next chunk: pull it into L2 now
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (k0 + 2 * kChunkK + j < prm.K)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (long long)(k0 + 2 * kChunkK + j) * prm.ldR));
-                }
                 mbar_wait(&bars->a_empty[ob], a_phase ^ 1);      // the MMAs that read this buffer have completed
                 tcgen05_fence_after();
                 uint32_t w[32];
@@ -532,7 +525,6 @@ int launch_cgemm3x_kloop(long long B, long long Nn, long long Mm, long long K, c
     prm.block_chunks = kloop_block_chunks(hybrid);
     prm.nblocks = (int)ceil_div(prm.kchunks, prm.block_chunks);
     prm.scratch = reinterpret_cast<float2*>(scratch);
-    prm.prefetch = getenv("SFA_KLOOP_PREFETCH") ? 1 : 0;      // measured: no gain, the extra LSU work costs ~7 %
     if (prm.nblocks > 1 && (!scratch || scratch_bytes < cgemm3x_kloop_scratch_bytes(K, hybrid) || ((uintptr_t)scratch & 7)))
         return SFA_ERR_WORKSPACE;
     const size_t smem = (size_t)kStages * kStageBytes + 2 * kPieceBytes + sizeof(Barriers) + 1024;

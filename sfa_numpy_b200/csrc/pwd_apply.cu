@@ -15,6 +15,7 @@
 //
 // c64 path: the GEMMs run on tcgen05 (cgemm3x_sm100.cu); c128 path: FP64 FMA kernels below.
 #include <stdlib.h>
+#include <mutex>
 #include "sfa_common.cuh"
 
 namespace sfa {
@@ -658,6 +659,10 @@ static SideStream* side_for_current_device() {
 
 static int pwd_steering_pipelined(const sfa_pwd_shape* s, const Plan& p, const double2* dd, const float2* x,
                                   float2* o, unsigned char* w, cudaStream_t st) {
+    // The side stream and its events are per device: calls from several host threads enqueue one after
+    // the other (the event waits are bound at enqueue time, so the GPU-side dependencies stay per call).
+    static std::mutex enqueue_mutex;
+    std::lock_guard<std::mutex> lock(enqueue_mutex);
     SideStream* ss = side_for_current_device();
     if (!ss) return SFA_ERR_CUDA;
     const long long L = s->L, Q = s->Q, T = s->T, F = s->F;
