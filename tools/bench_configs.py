@@ -8,7 +8,10 @@ from oracle import sfa_oracle as O
 from test_gpu_fullsize import CONFIGS
 CONFIGS = dict(CONFIGS, cfg3=("sph", 8, "ea3", 1024, 2562, 938, 0.042, "rigid", 100.0, "Tikh"))
 A, R, S = micarray.modal.angular, micarray.modal.radial, micarray.modal.steering
+ONLY = sys.argv[2].split(",") if len(sys.argv) > 2 else None     # e.g. cfg1,cfg2 (the steering form of cfg 5 takes 40 s)
 for name in sorted(CONFIGS):
+    if ONLY and name not in ONLY:
+        continue
     kind, N, grid, F, L, T, r, setup, a0, method = CONFIGS[name]
     if kind == "sph":
         az, co, w = (O.grid_equal_angle(N) if grid == "equal_angle" else O.grid_equal_angle(3) if grid == "ea3"
