@@ -112,3 +112,23 @@ def grid_equal_polar_angle(n):
     """Equi-angular sampling points on a circle (reference: angular.py:217-235)."""
     num_mic = 2 * n + 1
     return np.linspace(0, 2 * np.pi, num=num_mic, endpoint=False), np.ones(num_mic) / num_mic
+
+
+def grid_lebedev(n):
+    """Lebedev sampling points on a sphere (reference: angular.py:238-279).  Like the reference this
+    needs the optional `quadpy` package (the reference imports it lazily, angular.py:6-9, and fails with
+    a NameError without it; here the failure is an ImportError that says so).  Orders above 65 raise the
+    reference's ValueError."""
+    if n > 65:
+        raise ValueError("Maximum available Lebedev grid order is 65. "
+                         "(requested: {})".format(n))
+    try:
+        import quadpy
+    except ImportError as e:
+        raise ImportError("grid_lebedev needs the optional 'quadpy' package, as in the reference") from e
+    from warnings import warn
+    degrees = list(range(1, 32, 2)) + list(range(35, 132, 6))
+    q = quadpy.sphere.Lebedev(degree=[x for x in degrees if x >= 2 * n][0])
+    if np.any(q.weights < 0):
+        warn("Lebedev grid of order {} has negative weights.".format(n))
+    return q.azimuthal_polar[:, 0], q.azimuthal_polar[:, 1], 4 * np.pi * q.weights

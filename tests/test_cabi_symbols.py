@@ -107,3 +107,16 @@ def test_pwd_workspace_plan_without_gpu():
     # malformed shapes are rejected (0 bytes), not planned
     assert lib.sfa_pwd_work_bytes(_lib.PwdShape(8, 4, 4, 4, 9, 4, 1, 0, 0, 0)) == 0      # Cd^2 != M
     assert lib.sfa_pwd_work_bytes(_lib.PwdShape(8, 4, 4, 4, 9, 3, 1, 7, 0, 0)) == 0      # unknown precision
+
+
+def test_grid_lebedev_surface():
+    """angular.grid_lebedev exists with the reference's error behaviour (quadpy is optional there too)."""
+    import pytest
+    from sfa_numpy_b200.modal import angular
+    with pytest.raises(ValueError):
+        angular.grid_lebedev(66)
+    try:
+        import quadpy  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            angular.grid_lebedev(4)
