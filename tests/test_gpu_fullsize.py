@@ -29,8 +29,8 @@ CONFIGS = {
 }
 
 
-@pytest.mark.parametrize("name", list(CONFIGS))
-def test_full_size_config(name):
+@pytest.mark.parametrize("name,precision", [(n, "c64_fast") for n in CONFIGS] + [("cfg4", "c64"), ("cfg1", "c64")])
+def test_full_size_config(name, precision):
     import torch
     import sfa_numpy_b200 as micarray
     A, R, S = micarray.modal.angular, micarray.modal.radial, micarray.modal.steering
@@ -69,7 +69,7 @@ def test_full_size_config(name):
     g = torch.Generator(device="cuda").manual_seed(11)
     X1 = torch.randn((F, Q, T), dtype=torch.complex64, device="cuda", generator=g)
     X2 = torch.randn((F, Q, T), dtype=torch.complex64, device="cuda", generator=g)
-    plan = S.PwdPlan(Y_q, dn, Y_p, T, precision="c64_fast")
+    plan = S.PwdPlan(Y_q, dn, Y_p, T, precision=precision)
     q1 = plan(X1)
     assert tuple(q1.shape) == (F, L, T) and bool(torch.isfinite(torch.view_as_real(q1)).all())
     # spot bins against the oracle (factored form; dense reference chain is infeasible here)
