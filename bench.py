@@ -225,6 +225,20 @@ def cpu_baseline(O, cfg, azi, colat, w, azl, col, k):
             "stage3_outputs_per_s": outputs / best, "stage12_s": t_stage12}
 
 
+def parity_check(O, cfg, azi, colat, w, azl, col, k, Xh, out, bins):
+    """Compare `bins` of the beam tensor the timed loop just wrote with the CPU oracle (complex128
+    factored form).  Returns the worst normwise error per bin, max|q - ref| / max|ref|."""
+    Y_p = O.sht_matrix(cfg["N"], azi, colat, w)
+    Y_q = O.sht_matrix(cfg["N"], azl, col)
+    bn = O.spherical_pw(cfg["N"], k, cfg["r"], cfg["setup"])
+    dn, _ = O.regularize(1 / bn, cfg["a0"], cfg["method"])
+    ref = O.pwd_factored(Y_q, O.repeat_n_m(dn)[bins], Y_p, Xh[bins].astype(np.complex128))
+    got = out[bins].cpu().numpy()
+    errs = [float(np.max(np.abs(got[i] - ref[i])) / np.max(np.abs(ref[i]))) for i in range(len(bins))]
+    return {"bins": [int(b) for b in bins], "max_normwise_err": max(errs), "tolerance": 1e-5,
+            "oracle": "oracle.sfa_oracle.pwd_factored (complex128 NumPy) on the same X, after the timed loop"}
+
+
 def tensor_bound_configs(torch, micarray, O, dev, precision):
     """Stage 3 of the two tensor-bound BASELINE configs (cfg 4: N=16, 578 mics; cfg 5: N=32, 1089 mics) at
     full size -- the in-kernel K-loop GEMM (cgemm3x_kloop_sm100.cu) -- next to a cuBLAS TF32 GEMM timed
@@ -362,6 +376,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * F * L * T * args.steps / (ms * 1e-3)
+    # the output of the LAST timed step against the oracle: a fast step that computes something else is not a result
+    check_bins = [0, 74, F // 2 + 5, F - 1]
+    pcheck = parity_check(O, cfg, azi, colat, w, azl, col, k, Xh, out, check_bins)
+    if not (pcheck["max_normwise_err"] <= pcheck["tolerance"]):
+        raise SystemExit("bench: parity check failed: %r" % (pcheck,))
 
     # ---- dominant kernel: average launch duration with CUDA events on its launching stream ----
     lib.sfa_prof_enable(1)
@@ -372,20 +391,39 @@ def main():
     lib.sfa_prof_read(ctypes.byref(tot), ctypes.byref(cnt))
     lib.sfa_prof_enable(0)
     gemm_ms_per_step = tot.value / max(2, min(args.steps, 5))
-    # algorithmic bytes of the steering GEMM per step (complex64 I/O): X read + beams written +
-    # the steering matrices A_f it consumes  (DESIGN.md "roofline" section)
-    alg_bytes = 8.0 * F * T * (Q + L) + 8.0 * F * L * Q
+    # algorithmic bytes of stage 3 in complex64 I/O = spectra read + beams written + the two SH
+    # matrices + the radial filters.  The steering matrices A_f are this implementation's own intermediate
+    # and do NOT count.  Algorithmic flops = 8 F L Q T (steering form, Q < M).
+    M_modes, C_d = (N + 1) ** 2, N + 1
+    alg_bytes = 8.0 * F * T * (Q + L) + 8.0 * (Q + L) * M_modes + 8.0 * F * C_d
     alg_flops = 8.0 * F * L * Q * T
+    passes = 2 if args.precision == "c64_fast" else 3
     peaks, peak_src = load_peaks()
+    # tensor-side denominator: measured dense bf16 throughput / 2 = TF32 rate (sustained: the kernel runs
+    # inside a long step under the power cap); a tf32 pass and the bf16 pass of the hybrid mode take the same time
+    tf32_peak = 0.5 * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    t_hbm_ms = alg_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3
+    t_tensor_ms = alg_flops * passes / (tf32_peak * 1e12) * 1e3
     achieved = alg_bytes / (gemm_ms_per_step * 1e-3) / 1e9
     n_prof = max(2, min(args.steps, 5))
     launches_per_step = cnt.value / n_prof
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (74 bins) from the committed ncu
     # capture profiles/r1_i_cgemm3x_hybrid_2stage_ring2.txt; bench.py itself never runs under ncu.
     NCU_TRAFFIC_74_BINS = 1.377538e9 + 0.242853e9
-    roofline = {"kernel": "cgemm3x_kernel<%s> (tcgen05 steering GEMM)" % ("hybrid" if args.precision == "c64_fast" else "3xTF32"), "bound": "hbm",
+    step_ms = ms / args.steps
+    roofline = {"kernel": "stage-3 steering kernel, %s (tcgen05)" % ("hybrid TF32+BF16" if args.precision == "c64_fast" else "3xTF32"),
+                # `bound` / `frac` follow SURVEY 8(d): max(bytes / measured HBM, flops * passes / measured tensor) / t
+                "bound": "hbm" if t_hbm_ms >= t_tensor_ms else "tensor",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"],
+                "frac_hbm_kernel": t_hbm_ms / gemm_ms_per_step, "frac_hbm_step": t_hbm_ms / step_ms,
+                "frac_tensor_kernel": t_tensor_ms / gemm_ms_per_step, "frac_tensor_step": t_tensor_ms / step_ms,
+                "frac_max_rule_kernel": max(t_hbm_ms, t_tensor_ms) / gemm_ms_per_step,
+                "frac_max_rule_step": max(t_hbm_ms, t_tensor_ms) / step_ms,
+                "frac_step": t_hbm_ms / step_ms,
+                "t_hbm_ms": t_hbm_ms, "t_tensor_ms": t_tensor_ms, "tensor_passes": passes,
+                "tensor_peak_tflops": tf32_peak,
+                "tensor_peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 rate)",
                 "traffic": NCU_TRAFFIC_74_BINS if args.precision == "c64_fast" else None,
                 "traffic_source": "ncu --set full, one 74-bin launch (profiles/r1_i_cgemm3x_hybrid_2stage_ring2.txt)",
                 "alg_bytes_per_launch": alg_bytes / launches_per_step if launches_per_step else None,
@@ -402,7 +440,7 @@ def main():
             "config": {"workload": cfg["name"], "bins_per_gpu": F, "outputs_per_step_per_gpu": F * L * T,
                        "l2": "inputs+outputs (20 GB) far larger than L2; no flush needed",
                        "parallelism": "frequency-sharded x%d, no collective" % world},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "parity_check": pcheck}
 
     # ---- the collective of the multi-GPU path (north_star: "only an all-gather of the output beam maps") ----
     # Not inside `value` (each rank's beams stay resident); timed separately with CUDA events, max over ranks:

@@ -66,6 +66,13 @@ int sfa_version(void);
 /* number of SMs / compute capability of the current device (0 on success) */
 int sfa_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Library-wide tuning knobs (process-global, initialised once at load time from the SFA_<KEY> environment
+ * variables; no launch path calls getenv).  Keys: "pwd_chunk_mb" (scratch budget per frequency slab),
+ * "no_fused", "no_kloop", "no_cluster", "no_fold", "no_tma_store", "old_build" (0/1: switch a kernel
+ * variant off -- test and tuning use), "kloop_block", "issuers".  Unknown key: SFA_ERR_INVALID / NaN. */
+int sfa_set_option(const char* key, double value);
+double sfa_get_option(const char* key);
+
 /* Instrumentation used by bench.py: kernels launched by this library so far; optional
  * CUDA-event timing of the dominant kernel (the tcgen05 GEMM) on its launching stream. */
 long long sfa_launch_count(void);

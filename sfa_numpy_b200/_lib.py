@@ -30,6 +30,8 @@ SIGNATURES = {
     "sfa_last_cuda_error": (ctypes.c_char_p, []),
     "sfa_version": (c_int, []),
     "sfa_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
+    "sfa_set_option": (c_int, [ctypes.c_char_p, c_double]),
+    "sfa_get_option": (c_double, [ctypes.c_char_p]),
     "sfa_launch_count": (ctypes.c_longlong, []),
     "sfa_prof_enable": (c_int, [c_int]),
     "sfa_prof_read": (c_int, [ctypes.POINTER(c_double), ctypes.POINTER(ctypes.c_longlong)]),

@@ -462,10 +462,7 @@ cgemm3x_kloop_kernel(const __grid_constant__ CUtensorMap p_map, const Params prm
 // Accumulation block (in 32-k chunks): keeps the truncation bias of the tensor-core accumulate at
 // ~6e-6 of the result through both GEMMs of the factored form (measured 2.1e-8 / 3.2e-8 per k).
 static int kloop_block_chunks(int hybrid) {
-    if (const char* e = getenv("SFA_KLOOP_BLOCK")) {
-        const int v = atoi(e);
-        if (v > 0) return v;
-    }
+    if (options().kloop_block > 0) return options().kloop_block;
     return hybrid ? 9 : 6;
 }
 
@@ -516,7 +513,7 @@ int launch_cgemm3x_kloop(long long B, long long Nn, long long Mm, long long K, c
     prm.rowscale = rowscale;
     prm.strideS = strideS;
     const long long m_tiles = ceil_div(prm.rows, kTileM);
-    const int csize = (m_tiles >= 2 && !getenv("SFA_NO_CLUSTER")) ? 2 : 1;
+    const int csize = (m_tiles >= 2 && !options().no_cluster) ? 2 : 1;
     prm.csize = csize;
     prm.m_groups = (int)ceil_div(m_tiles, csize);
     prm.n_tiles = (int)ceil_div(Nn, kTileN);
@@ -528,12 +525,8 @@ int launch_cgemm3x_kloop(long long B, long long Nn, long long Mm, long long K, c
     if (prm.nblocks > 1 && (!scratch || scratch_bytes < cgemm3x_kloop_scratch_bytes(K, hybrid) || ((uintptr_t)scratch & 7)))
         return SFA_ERR_WORKSPACE;
     const size_t smem = (size_t)kStages * kStageBytes + 2 * kPieceBytes + sizeof(Barriers) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SFA_CUDA_CHECK(cudaFuncSetAttribute(cgemm3x_kloop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SFA_CUDA_CHECK(cudaFuncSetAttribute(cgemm3x_kloop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    if (hybrid) SFA_ENSURE_DYN_SMEM(cgemm3x_kloop_kernel<true>, smem);
+    else SFA_ENSURE_DYN_SMEM(cgemm3x_kloop_kernel<false>, smem);
     const long long max_clusters = sm_count() / csize;
     const long long grid = (prm.tasks < max_clusters ? prm.tasks : max_clusters) * csize;
     cudaLaunchConfig_t cfg = {};

@@ -533,9 +533,9 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     // Small m extents with a shared P (factored form at small T): fold batches into the m-tiles.
     // Only for single-pass products: the split-K accumulate passes rely on the TMA reduce-add store,
     // which needs whole tiles inside one batch (measured: folding + register read-modify-write is slower).
-    const int fold = (p_shared && Mm <= 64 && B > 1 && out_mode == OUT_C64 && !getenv("SFA_NO_FOLD")) ? 1 : 0;
+    const int fold = (p_shared && Mm <= 64 && B > 1 && out_mode == OUT_C64 && !options().no_fold) ? 1 : 0;
     const int tma_store = (!fold && (ldo & 1) == 0 && (strideO & 1) == 0 && (((uintptr_t)out) & 15) == 0 &&
-                           !getenv("SFA_NO_TMA_STORE")) ? 1 : 0;
+                           !options().no_tma_store) ? 1 : 0;
     CUtensorMap omap = map;
     if (tma_store) {
         cuuint64_t odim[3] = {(cuuint64_t)(2 * Mm), (cuuint64_t)Nn, (cuuint64_t)B};
@@ -576,14 +576,10 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     prm.tasks = B * prm.m_tiles;
     prm.n_tiles = (int)ceil_div(Nn, kTileN);
     const size_t smem = (size_t)kStagesB * kStageBytes + 2 * kStoreRing * kStoreBytes + sizeof(Barriers) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SFA_CUDA_CHECK(cudaFuncSetAttribute(cgemm3x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SFA_CUDA_CHECK(cudaFuncSetAttribute(cgemm3x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    if (hybrid) SFA_ENSURE_DYN_SMEM(cgemm3x_kernel<true>, smem);
+    else SFA_ENSURE_DYN_SMEM(cgemm3x_kernel<false>, smem);
     // CTA pairs share the P stream by TMA multicast whenever a batch has at least two m-tiles.
-    const int csize = (prm.m_tiles >= 2 && !getenv("SFA_NO_CLUSTER")) ? 2 : 1;
+    const int csize = (prm.m_tiles >= 2 && !options().no_cluster) ? 2 : 1;
     prm.csize = csize;
     prm.m_groups = (prm.m_tiles + csize - 1) / csize;
     const long long n_groups = (fold ? 1 : B) * prm.m_groups;
@@ -593,7 +589,7 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     cfg.gridDim = dim3((unsigned)grid);
     // One issuer warp is enough (measured: a second one, splitting Re/Im, changes nothing) and keeps
     // the CTA at 448 threads x 128 registers, which leaves room for a steering-build CTA on the SM.
-    prm.issuers = (getenv("SFA_ISSUERS") && atoi(getenv("SFA_ISSUERS")) == 2) ? 2 : 1;
+    prm.issuers = options().issuers == 2 ? 2 : 1;
     cfg.blockDim = dim3(prm.issuers == 2 ? kThreads : kThreads - 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;

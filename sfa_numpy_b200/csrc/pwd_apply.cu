@@ -31,7 +31,7 @@ int launch_cgemm3x_kloop(long long B, long long Nn, long long Mm, long long K, c
                          void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t cgemm3x_kloop_scratch_bytes(long long K, int hybrid);
 
-static inline bool use_kloop(long long K, int p_shared) { return K > 64 && p_shared && !getenv("SFA_NO_KLOOP"); }
+static inline bool use_kloop(long long K, int p_shared) { return K > 64 && p_shared && !options().no_kloop; }
 
 constexpr int kOutC64 = 0, kOutFirstOfMany = 1, kOutAccum = 2;
 
@@ -270,7 +270,7 @@ static int launch_steer_build(const float2* G, const float2* d, int Cd, long lon
                               int hybrid, float* A, cudaStream_t st) {
     const dim3 grid((unsigned)ceil_div(LQ / 2, 128), (unsigned)ceil_div(nf, 8));
     prof_aux_begin(st);
-    if (Cd <= 16 && !getenv("SFA_OLD_BUILD")) {
+    if (Cd <= 16 && !options().old_build) {
         // ~8 CTAs per SM in flight; G is re-read once per `bpc` bins
         const int E = Cd <= 9 ? 4 : 2;
         const long long gx = ceil_div(LQ / E, 128);
@@ -473,8 +473,7 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
     p->form = form;
     // bins per chunk: keep the per-chunk scratch around `budget` bytes and the task count a
     // multiple of the SM count (tasks = bins * ceil(T/128)) so persistent CTAs finish together.
-    double budget = 256.0 * 1024 * 1024;   // per slab
-    if (const char* e = getenv("SFA_PWD_CHUNK_MB")) budget = atof(e) * 1024 * 1024;
+    const double budget = options().pwd_chunk_mb * 1024 * 1024;   // per slab
     const double per_bin = (form == 1) ? (double)s->L * p->Qp * 16.0 : (double)s->M * p->Tld * (c64 ? 8.0 : 16.0);
     const long long m_tiles = ceil_div(s->T, 128);
     const long long base = sm_count() / gcdll(sm_count(), m_tiles);
@@ -767,20 +766,30 @@ extern "C" int sfa_pwd_host_create(sfa_pwd_host_ctx** out_ctx, const sfa_pwd_sha
     c->chunk = chunk;
     c->operators_set = false;
     const size_t eb = elem_bytes(s);
-    SFA_CUDA_CHECK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-    SFA_CUDA_CHECK(cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking));
-    SFA_CUDA_CHECK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-        SFA_CUDA_CHECK(cudaEventCreateWithFlags(&c->in_done[i], cudaEventDisableTiming));
-        SFA_CUDA_CHECK(cudaEventCreateWithFlags(&c->cmp_done[i], cudaEventDisableTiming));
-        SFA_CUDA_CHECK(cudaEventCreateWithFlags(&c->out_done[i], cudaEventDisableTiming));
-        SFA_CUDA_CHECK(cudaMalloc(&c->d_X[i], (size_t)chunk * s->Q * s->T * eb));
-        SFA_CUDA_CHECK(cudaMalloc(&c->d_O[i], (size_t)chunk * s->L * s->out_ld * eb));
+    // every handle starts out null (value-initialised ctx), so a failure half-way releases exactly
+    // what exists: sfa_pwd_host_destroy skips null handles
+    rc = [&]() -> int {
+        SFA_CUDA_CHECK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        SFA_CUDA_CHECK(cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking));
+        SFA_CUDA_CHECK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SFA_CUDA_CHECK(cudaEventCreateWithFlags(&c->in_done[i], cudaEventDisableTiming));
+            SFA_CUDA_CHECK(cudaEventCreateWithFlags(&c->cmp_done[i], cudaEventDisableTiming));
+            SFA_CUDA_CHECK(cudaEventCreateWithFlags(&c->out_done[i], cudaEventDisableTiming));
+            SFA_CUDA_CHECK(cudaMalloc(&c->d_X[i], (size_t)chunk * s->Q * s->T * eb));
+            SFA_CUDA_CHECK(cudaMalloc(&c->d_O[i], (size_t)chunk * s->L * s->out_ld * eb));
+        }
+        SFA_CUDA_CHECK(cudaMalloc(&c->d_YL, (size_t)s->L * s->M * 16));
+        SFA_CUDA_CHECK(cudaMalloc(&c->d_YQ, (size_t)s->Q * s->M * 16));
+        SFA_CUDA_CHECK(cudaMalloc(&c->d_d, (size_t)(s->F > 0 ? s->F : 1) * s->Cd * 16));
+        SFA_CUDA_CHECK(cudaMalloc(&c->d_work, c->plan.total));
+        return SFA_OK;
+    }();
+    if (rc != SFA_OK) {
+        sfa_pwd_host_destroy(c);
+        cudaGetLastError();             // the error is reported through rc / sfa_last_cuda_error
+        return rc;
     }
-    SFA_CUDA_CHECK(cudaMalloc(&c->d_YL, (size_t)s->L * s->M * 16));
-    SFA_CUDA_CHECK(cudaMalloc(&c->d_YQ, (size_t)s->Q * s->M * 16));
-    SFA_CUDA_CHECK(cudaMalloc(&c->d_d, (size_t)(s->F > 0 ? s->F : 1) * s->Cd * 16));
-    SFA_CUDA_CHECK(cudaMalloc(&c->d_work, c->plan.total));
     *out_ctx = c;
     return SFA_OK;
 }
@@ -847,19 +856,19 @@ extern "C" int sfa_pwd_host_destroy(sfa_pwd_host_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < 2; ++i) {
-        cudaFree(c->d_X[i]);
-        cudaFree(c->d_O[i]);
-        cudaEventDestroy(c->in_done[i]);
-        cudaEventDestroy(c->cmp_done[i]);
-        cudaEventDestroy(c->out_done[i]);
+        if (c->d_X[i]) cudaFree(c->d_X[i]);
+        if (c->d_O[i]) cudaFree(c->d_O[i]);
+        if (c->in_done[i]) cudaEventDestroy(c->in_done[i]);
+        if (c->cmp_done[i]) cudaEventDestroy(c->cmp_done[i]);
+        if (c->out_done[i]) cudaEventDestroy(c->out_done[i]);
     }
-    cudaFree(c->d_YL);
-    cudaFree(c->d_YQ);
-    cudaFree(c->d_d);
-    cudaFree(c->d_work);
-    cudaStreamDestroy(c->s_in);
-    cudaStreamDestroy(c->s_cmp);
-    cudaStreamDestroy(c->s_out);
+    if (c->d_YL) cudaFree(c->d_YL);
+    if (c->d_YQ) cudaFree(c->d_YQ);
+    if (c->d_d) cudaFree(c->d_d);
+    if (c->d_work) cudaFree(c->d_work);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     delete c;
     return SFA_OK;
 }

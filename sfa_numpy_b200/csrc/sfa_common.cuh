@@ -40,4 +40,36 @@ void prof_aux_end(cudaStream_t st);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Function attributes are PER DEVICE: the dynamic-shared-memory opt-in is remembered per (call site,
+// device), so a process that drives several GPUs opts in on each of them.
+static inline int current_device() {
+    int dev = -1;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+#define SFA_ENSURE_DYN_SMEM(kern, bytes)                                                                   \
+    do {                                                                                                   \
+        static size_t _optin[64] = {0};                                                                    \
+        const int _dev = ::sfa::current_device();                                                          \
+        const bool _known = _dev >= 0 && _dev < 64;                                                        \
+        if ((size_t)(bytes) > 48 * 1024 && (!_known || (size_t)(bytes) > _optin[_dev])) {                  \
+            SFA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            if (_known) _optin[_dev] = (size_t)(bytes);                                                    \
+        }                                                                                                  \
+    } while (0)
+
+// Library-wide tuning knobs (sfa_set_option / sfa_get_option of the C ABI).  Initialised ONCE, at load
+// time, from the SFA_* environment variables of the same meaning; launches never call getenv().
+struct Options {
+    double pwd_chunk_mb;   // per-slab scratch budget of the chunked stage-3 paths (MiB)
+    int no_kloop;          // K > 64 with a shared left operand: split-K launches instead of the K-loop kernel
+    int no_cluster;        // no CTA pairs / TMA multicast
+    int no_fold;           // resident-K kernel: do not fold bins into the frame tiles
+    int no_tma_store;      // resident-K kernel: register stores instead of the TMA-store epilogue
+    int kloop_block;       // accumulation block of the K-loop kernel in 32-k chunks (0 = default)
+    int issuers;           // MMA issuer warps of the resident-K kernel (1 or 2)
+    int old_build;         // steering build: generic kernel instead of the few-groups fast kernel
+    int no_fused;          // steering form: slab build + GEMM launches instead of the fused persistent kernel
+};
+Options& options();
+
 }  // namespace sfa

@@ -1,4 +1,5 @@
 // Status strings, device query, pinned-memory helpers of the C ABI.
+#include <stdlib.h>
 #include <string.h>
 #include <utility>
 #include <vector>
@@ -21,6 +22,31 @@ int sm_count() {
     }
     return cached[dev];
 }
+// ---- tuning knobs: environment read once (static initialisation at library load) ----
+static double env_num(const char* name, double dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atof(e) : dflt;
+}
+static int env_flag(const char* name) {
+    const char* e = getenv(name);
+    return (e && *e && strcmp(e, "0") != 0) ? 1 : 0;
+}
+static Options make_options() {
+    Options o;
+    o.pwd_chunk_mb = env_num("SFA_PWD_CHUNK_MB", 256.0);
+    o.no_kloop = env_flag("SFA_NO_KLOOP");
+    o.no_cluster = env_flag("SFA_NO_CLUSTER");
+    o.no_fold = env_flag("SFA_NO_FOLD");
+    o.no_tma_store = env_flag("SFA_NO_TMA_STORE");
+    o.kloop_block = (int)env_num("SFA_KLOOP_BLOCK", 0.0);
+    o.issuers = ((int)env_num("SFA_ISSUERS", 1.0) == 2) ? 2 : 1;
+    o.old_build = env_flag("SFA_OLD_BUILD");
+    o.no_fused = env_flag("SFA_NO_FUSED");
+    return o;
+}
+static Options g_options = make_options();
+Options& options() { return g_options; }
+
 static long long g_launches = 0;
 void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
 long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
@@ -144,6 +170,38 @@ int sfa_prof_timeline(double* rows, int max_rows) {
         }
     }
     return n;
+}
+
+// Tuning knobs (process-global).  Unknown key -> SFA_ERR_INVALID / NaN.
+static double* option_slot(const char* key, int** islot) {
+    sfa::Options& o = sfa::options();
+    *islot = nullptr;
+    if (!key) return nullptr;
+    if (!strcmp(key, "pwd_chunk_mb")) return &o.pwd_chunk_mb;
+    if (!strcmp(key, "no_kloop")) *islot = &o.no_kloop;
+    else if (!strcmp(key, "no_cluster")) *islot = &o.no_cluster;
+    else if (!strcmp(key, "no_fold")) *islot = &o.no_fold;
+    else if (!strcmp(key, "no_tma_store")) *islot = &o.no_tma_store;
+    else if (!strcmp(key, "kloop_block")) *islot = &o.kloop_block;
+    else if (!strcmp(key, "issuers")) *islot = &o.issuers;
+    else if (!strcmp(key, "old_build")) *islot = &o.old_build;
+    else if (!strcmp(key, "no_fused")) *islot = &o.no_fused;
+    return nullptr;
+}
+int sfa_set_option(const char* key, double value) {
+    int* is = nullptr;
+    double* ds = option_slot(key, &is);
+    if (ds) *ds = value;
+    else if (is) *is = (int)value;
+    else return SFA_ERR_INVALID;
+    return SFA_OK;
+}
+double sfa_get_option(const char* key) {
+    int* is = nullptr;
+    double* ds = option_slot(key, &is);
+    if (ds) return *ds;
+    if (is) return (double)*is;
+    return __builtin_nan("");
 }
 
 const char* sfa_strerror(int status) {

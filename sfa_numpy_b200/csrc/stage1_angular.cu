@@ -162,8 +162,7 @@ static int launch_sht(int N, long long Q, const double* azi, const double* colat
                       const double* w, double2* Y, cudaStream_t st) {
     const size_t smem = (size_t)((N + 1) * (N + 2) / 2) * sizeof(double2) + (size_t)(N + 1) * sizeof(double);
     if (smem > 200 * 1024) return SFA_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024)
-        SFA_CUDA_CHECK(cudaFuncSetAttribute(sht_matrix_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SFA_ENSURE_DYN_SMEM(sht_matrix_kernel<G>, smem);
     const int threads = 256;
     const long long warps_needed = ceil_div(Q, 32 / G);
     long long blocks = ceil_div(warps_needed, threads / 32);
@@ -201,11 +200,7 @@ extern "C" int sfa_cht_matrix(int N, int64_t Q, const double* pol, const double*
     const size_t per_warp = (size_t)32 * (2 * N + 1) * sizeof(double2);
     if (Q >= 4096 && N >= 1 && N <= 256 && per_warp * 4 <= 200 * 1024) {
         const size_t smem = per_warp * 4;
-        static size_t attr_bytes = 0;
-        if (smem > 48 * 1024 && smem > attr_bytes) {
-            SFA_CUDA_CHECK(cudaFuncSetAttribute(sfa::cht_matrix_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_bytes = smem;
-        }
+        SFA_ENSURE_DYN_SMEM(sfa::cht_matrix_rows_kernel, smem);
         long long rblocks = sfa::ceil_div(sfa::ceil_div(Q, 32), 4);
         const long long rcap = (long long)sfa::sm_count() * 8;
         if (rblocks > rcap) rblocks = rcap;

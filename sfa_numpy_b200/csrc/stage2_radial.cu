@@ -92,11 +92,12 @@ radial_filter_kernel(int N, long long F, const double* __restrict__ k, double r,
             if (is_zero_entry(b)) {
                 local_zero += mirror ? 2 : 1;
                 if (want_zero_list) {
+                    // every slot below the cap is written (a mirrored pair may straddle it); find/apply
+                    // do nothing once the overflow flag is up, so no unwritten slot is ever read
                     const int slot = atomicAdd(&status[3], mirror ? 2 : 1);
-                    if (slot + (mirror ? 1 : 0) < kWorklistCap) {
-                        worklist[slot] = g;
-                        if (mirror) worklist[slot + 1] = gm;
-                    } else status[2] = 1;
+                    if (slot < kWorklistCap) worklist[slot] = g;
+                    if (mirror && slot + 1 < kWorklistCap) worklist[slot + 1] = gm;
+                    if (slot + (mirror ? 1 : 0) >= kWorklistCap) status[2] = 1;
                 }
             }
             if (method >= 0) {
@@ -130,6 +131,7 @@ find_replacement_kernel(long long F, int C, const double* __restrict__ kr,
     // scan the F rows of the column, then a warp-shuffle + shared-memory argmin.
     __shared__ double s_best[8], s_bestk[8];
     __shared__ long long s_besti[8];
+    if (status[2]) return;                                  // worklist overflow: reported by the host layer
     const int nlist = min((long long)status[3], kWorklistCap);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     for (long long e = blockIdx.x; e < nlist; e += gridDim.x) {
@@ -186,7 +188,7 @@ __global__ void apply_replacement_kernel(int C, int method, double a0, double al
                                          const int* __restrict__ status,
                                          const long long* __restrict__ worklist) {
     const int nlist = min((long long)status[3], kWorklistCap);
-    if (status[1]) return;
+    if (status[1] || status[2]) return;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nlist;
          e += (long long)gridDim.x * blockDim.x) {
         const long long g = worklist[e];
@@ -328,7 +330,7 @@ extern "C" int sfa_radial_filter(int kind, int N, int64_t F, const double* k, do
 #define SFA_RADIAL_CASE(FAM, SET, SCL)                                                                         \
     if (family == FAM && setup == SET && scale == SCL) {                                                       \
         auto kern = radial_filter_kernel<FAM, SET, SCL>;                                                       \
-        SFA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        SFA_ENSURE_DYN_SMEM(kern, smem);                                                                       \
         kern<<<(unsigned)blocks, T, smem, st>>>(N, F, k, r, rs, replace_zeros ? 1 : 0, method, a0, alpha,      \
                                                  reinterpret_cast<double2*>(bn), reinterpret_cast<double2*>(dn), \
                                                  hr, hc, status, wl);                                          \

@@ -41,22 +41,32 @@ class _DeferredChecks:
     def add(self, status):
         # pinned buffers are recycled: cudaHostAlloc per call would cost more than the kernels
         host = self.pool.pop() if self.pool else torch.empty(4, dtype=torch.int32, pin_memory=True)
-        host.copy_(status, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
+        # copy and event go to the stream of the tensor's OWN device (which need not be the current one)
+        with torch.cuda.device(status.device):
+            host.copy_(status, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(status.device))
         self.pending.append((ev, host))
 
     def flush(self, wait=False):
-        keep = []
-        for ev, host in self.pending:
-            if not wait and not ev.query():
-                keep.append((ev, host))
+        """Validate every status word that has landed (all of them with wait=True).  An entry leaves the
+        pending list BEFORE it can raise, so one failed call is reported exactly once; entries that are
+        not ready yet are re-queued; if several failed, the first is raised and the rest stay queued."""
+        pending, self.pending = self.pending, []
+        error = None
+        for ev, host in pending:
+            if error is not None or (not wait and not ev.query()):
+                self.pending.append((ev, host))
                 continue
             ev.synchronize()
             st = host.tolist()
             self.pool.append(host)
-            _raise_for_status(st)
-        self.pending = keep
+            try:
+                _raise_for_status(st)
+            except (ValueError, RuntimeError) as e:
+                error = e
+        if error is not None:
+            raise error
 
 
 _deferred = _DeferredChecks()
@@ -64,12 +74,7 @@ _deferred = _DeferredChecks()
 
 def check_deferred():
     """Wait for and validate every deferred zero-replacement status (see `check="defer"`)."""
-    pending, _deferred.pending = _deferred.pending, []
-    for ev, host in pending:
-        ev.synchronize()
-        st = host.tolist()
-        _deferred.pool.append(host)
-        _raise_for_status(st)
+    _deferred.flush(wait=True)
 
 
 def _raise_for_status(st):
@@ -103,8 +108,10 @@ def _radial(kind, N, k, r, rs, setup, replace_zeros, method=None, a0=0.0, check=
                                          _lib.ptr(hn), _lib.ptr(status), _lib.ptr(work), _lib.stream_ptr(dev)))
     if replace_zeros:
         if check == "defer":
-            _deferred.flush()
+            # queue this call's status FIRST: an error of an earlier call raised by flush() must not
+            # lose it (the kernel has already been launched and its result is valid)
             _deferred.add(status)
+            _deferred.flush()
         else:
             _raise_for_status(status.tolist())
     return bn, dn, hn

@@ -39,6 +39,22 @@ def _shape_of(Y_look, dn, Y_mic, F, Q, T, precision, form):
     return _lib.PwdShape(F, L, Q, T, M, Cd, per_order, PRECISIONS[precision], FORMS[form], 0)
 
 
+_C64_DN_LIMIT = 1e30
+
+
+def _check_c64_range(dn, precision):
+    """The complex64 paths narrow the radial filters to float32.  Un-regularised filters (method 'none', or a
+    huge a0) reach |1/b_n| ~ 1e47 at high orders and small kr, which is Inf in float32
+    and would turn into NaN beams silently; the reference computes that case in complex128.  One tiny
+    reduction + host read per plan / one-shot call -- not on the per-step path."""
+    if precision == "c128" or dn.numel() == 0:
+        return
+    a = torch.view_as_real(dn).abs()
+    if not bool(torch.isfinite(a).all()) or float(a.max()) > _C64_DN_LIMIT:
+        raise ValueError("radial filters exceed the float32 range of the complex64 paths (max |dn| > 1e30 or "
+                         "non-finite): regularise them (radial.regularize) or use precision='c128'")
+
+
 def _padded_pitch(T):
     """Row pitch (in frames) of the beam tensor: multiples of 32 frames (256 B) keep every 128-byte
     line of a row tile inside one CTA, worth ~1.4x of HBM write bandwidth (stage 3)."""
@@ -126,6 +142,7 @@ def pwd(Y_look, dn, Y_mic, p, precision=None, form="auto", out=None):
         raise ValueError("p must have shape (F, Q) or (F, Q, T)")
     F, Q, T = X.shape
     shape = _shape_of(Y_look, dn, Y_mic, F, Q, T, precision, form)
+    _check_c64_range(dn, precision)
     L = Y_look.shape[0]
     if out is None:
         out = _alloc_out(F, L, T, cdtype, dev)
@@ -171,6 +188,7 @@ class PwdPlan:
         self.dn = dn[None, :] if dn.ndim == 1 else dn
         F, Q = self.dn.shape[0], self.Y_mic.shape[0]
         self.shape = _shape_of(self.Y_look, self.dn, self.Y_mic, F, Q, int(T), precision, form)
+        _check_c64_range(self.dn, precision)      # checked once per plan; re-assigned `dn` is the caller's business
         self.nbytes = self.lib.sfa_pwd_work_bytes(ctypes.byref(self.shape))
         if self.nbytes == 0:
             raise ValueError("unsupported plane-wave-decomposition shape")

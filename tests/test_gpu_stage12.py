@@ -140,20 +140,44 @@ def test_regularize(mic, golden, method):
         R.regularize(g["reg_dn"], 1.0, "tikhonov")
 
 
-@pytest.mark.parametrize("method", ["softclip", "Tikh", "hardclip"])
+@pytest.mark.parametrize("method", O.METHODS)
 def test_fused_radial_filters(mic, method):
-    """bn, dn, hn from ONE kernel == reference sequence spherical_pw -> regularize(1/bn)."""
+    """bn, dn, hn from ONE kernel == reference sequence spherical_pw -> regularize(1/bn), for all six
+    regularisers (radial.py:240-266): both branches of the fused inverse (one-division closed form for
+    none/Tikh/wng, Smith division for the clipping methods) and both hn store types (complex for
+    none/discard/hardclip, real otherwise)."""
     k = O.wavenumbers(1024)
     bn, dn, hn = mic.modal.radial.radial_filters(8, k, 0.042, "rigid", 100.0, method)
     ref_b = O.spherical_pw(8, k, 0.042, "rigid")
-    ref_d, ref_h = O.regularize(1 / ref_b, 100.0, method)
+    with np.errstate(all="ignore"):
+        ref_d, ref_h = O.regularize(1 / ref_b, 100.0, method)
     assert_close(cpu(bn), ref_b, **TOL, name="bn")
     assert_close(cpu(dn), ref_d, **TOL, name="dn")
     assert_close(cpu(hn), ref_h, **TOL, name="hn")
+    assert cpu(hn).dtype == ref_h.dtype
     bn, dn, hn = mic.modal.radial.radial_filters(16, k, 0.1, "open", 3000.0, method, kind="circular_pw")
     ref_b = O.circular_pw(16, k, 0.1, "open")
-    ref_d, ref_h = O.regularize(1 / ref_b, 3000.0, method)
+    with np.errstate(all="ignore"):
+        ref_d, ref_h = O.regularize(1 / ref_b, 3000.0, method)
     assert_close(cpu(dn), ref_d, **TOL, name="cdn")
+    assert_close(cpu(hn), ref_h, **TOL, name="chn")
+    assert cpu(hn).dtype == ref_h.dtype
+
+
+@pytest.mark.parametrize("method", O.METHODS)
+def test_cfg4_radial_all_methods(mic, method):
+    """cardioid sphere N=16, kr = geomspace(0.01, 50, 1024) (min |b_n| ~ 2.5e-48,
+    1/b ~ 4e47), every regulariser, through the fused kernel."""
+    r = 0.1
+    k = np.geomspace(0.01, 50, 1024) / r
+    bn, dn, hn = mic.modal.radial.radial_filters(16, k, r, "card", 100.0, method)
+    ref_b = O.spherical_pw(16, k, r, "card")
+    with np.errstate(all="ignore"):
+        ref_d, ref_h = O.regularize(1 / ref_b, 100.0, method)
+    assert_close(cpu(bn), ref_b, **TOL, name="bn")
+    assert_close(cpu(dn), ref_d, **TOL, name="dn")
+    assert_close(cpu(hn), ref_h, **TOL, name="hn")
+    assert cpu(hn).dtype == ref_h.dtype
 
 
 def test_mode_matrices(mic, golden):

@@ -256,7 +256,7 @@ def _host_path_case(S, T, N=4, grid=None):
 
 
 @pytest.mark.parametrize("precision", ["c64", "c64_fast", "c128"])
-def test_pwd_many_chunks(mic, monkeypatch, precision):
+def test_pwd_many_chunks(mic, precision):
     """Force a tiny per-chunk scratch budget so the bins are processed in many chunks (for the
     steering form this is the side-stream pipeline build(i+1) || gemm(i)); results must not change."""
     import torch
@@ -270,13 +270,19 @@ def test_pwd_many_chunks(mic, monkeypatch, precision):
     cd = torch.complex128 if precision == "c128" else torch.complex64
     g = torch.Generator(device="cuda").manual_seed(1)
     X = torch.randn((F, Q, T), dtype=cd, device="cuda", generator=g)
-    for form in ("steering", "factored"):
-        monkeypatch.delenv("SFA_PWD_CHUNK_MB", raising=False)
-        q_one = S.pwd(Y_q, dn, Y_p, X, precision=precision, form=form)
-        monkeypatch.setenv("SFA_PWD_CHUNK_MB", "0.5")
-        q_many = S.pwd(Y_q, dn, Y_p, X, precision=precision, form=form)
-        torch.cuda.synchronize()
-        assert torch.equal(q_one, q_many), form
+    from sfa_numpy_b200 import _lib
+    lib = _lib.load()
+    default_mb = lib.sfa_get_option(b"pwd_chunk_mb")
+    try:
+        for form in ("steering", "factored"):
+            q_one = S.pwd(Y_q, dn, Y_p, X, precision=precision, form=form)
+            _lib.check(lib.sfa_set_option(b"pwd_chunk_mb", 0.5))
+            q_many = S.pwd(Y_q, dn, Y_p, X, precision=precision, form=form)
+            _lib.check(lib.sfa_set_option(b"pwd_chunk_mb", default_mb))
+            torch.cuda.synchronize()
+            assert torch.equal(q_one, q_many), form
+    finally:
+        lib.sfa_set_option(b"pwd_chunk_mb", default_mb)
     Yp_ref, Yq_ref = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
     dn_ref, _ = O.regularize(1 / O.spherical_pw(N, k, 0.042, "rigid"), 100, "softclip")
     ref = O.pwd_factored(Yq_ref, O.repeat_n_m(dn_ref), Yp_ref, cpu(X).astype(np.complex128))

@@ -3,6 +3,8 @@ sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import numpy as np, torch
 import sfa_numpy_b200 as micarray
 from oracle import sfa_oracle as O
+from sfa_numpy_b200 import _lib
+lib = _lib.load()
 A, R, S = micarray.modal.angular, micarray.modal.radial, micarray.modal.steering
 def bin_err(q, ref):
     q = q.reshape(q.shape[0], -1); ref = ref.reshape(ref.shape[0], -1)
@@ -17,13 +19,10 @@ for (N, Q, L, F, T, r, setup) in ((32, 1089, 16384, 64, 32, 0.2, "rigid"), (16, 
     ref = O.pwd_factored(Y_q.cpu().numpy(), O.repeat_n_m(dn.cpu().numpy())[sel], Y_p.cpu().numpy(), X[sel].cpu().numpy().astype(np.complex128))
     for prec in ("c64", "c64_fast"):
         for env in ("", "1"):
-            if env: os.environ["SFA_NO_KLOOP"] = "1"
-            else: os.environ.pop("SFA_NO_KLOOP", None)
+            lib.sfa_set_option(b"no_kloop", 1.0 if env else 0.0)
             q = S.pwd(Y_q, dn, Y_p, X, precision=prec, form="factored")
             print("N=%d %s %s: bin_err %.3e" % (N, prec, "splitK" if env else "kloop", bin_err(q[sel].cpu().numpy(), ref)))
 # random-data GEMM error vs K
-from sfa_numpy_b200 import _lib
-lib = _lib.load()
 rng = np.random.default_rng(0)
 for K in (64, 128, 289, 578, 1089, 2048):
     B, Nn, Mm = 4, 256, 32
@@ -35,8 +34,7 @@ for K in (64, 128, 289, 578, 1089, 2048):
     res = []
     for hybrid in (0, 1):
         for env in ("", "1"):
-            if env: os.environ["SFA_NO_KLOOP"] = "1"
-            else: os.environ.pop("SFA_NO_KLOOP", None)
+            lib.sfa_set_option(b"no_kloop", 1.0 if env else 0.0)
             _lib.check(lib.sfa_cgemm3x(B, Nn, Mm, K, _lib.ptr(P), K, 0, _lib.ptr(Rt), Mm, K * Mm, _lib.ptr(out), Mm, Nn * Mm, None, Nn, hybrid, _lib.stream_ptr()))
             e = out.cpu().numpy() - ref
             res.append("%s/%s max %.2e rms %.2e" % ("hyb" if hybrid else "3x", "splitK" if env else "kloop", np.max(np.abs(e)) / np.max(np.abs(ref)), np.sqrt(np.mean(np.abs(e)**2) / np.mean(np.abs(ref)**2))))
