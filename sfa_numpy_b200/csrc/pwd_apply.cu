@@ -31,6 +31,15 @@ int launch_cgemm3x_kloop(long long B, long long Nn, long long Mm, long long K, c
                          void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t cgemm3x_kloop_scratch_bytes(long long K, int hybrid);
 
+// fused steering kernel (pwd_fused_sm100.cu): A_f built in tensor memory, one persistent launch
+bool pwd_fused_supported(long long L, long long Q, long long T, int Cd, long long out_ld, const void* out);
+size_t pwd_fused_g2_bytes(long long L, long long Q, int Cd);
+size_t pwd_fused_xs_bytes(long long nf, long long Q, long long T);
+int launch_group_products_g2(const double2* YL, const double2* YQt, long long L, long long Q, int M, int Cd,
+                             int per_order, float* G2, cudaStream_t st);
+int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd, const float* G2, const float2* d,
+                     const float2* X, float* Xs, float2* out, long long ldo, int hybrid, cudaStream_t st);
+
 static inline bool use_kloop(long long K, int p_shared) { return K > 64 && p_shared && !options().no_kloop; }
 
 constexpr int kOutC64 = 0, kOutFirstOfMany = 1, kOutAccum = 2;
@@ -418,6 +427,8 @@ static long long gcdll(long long a, long long b) { return b ? gcdll(b, a % b) : 
 
 struct Plan {
     int form;
+    int fused;                  // form 1 through the fused persistent kernel (no steering slabs)
+    size_t off_G2, off_Xs;
     long long Qp, Mp, Tld, Old; // padded k extents / leading dims (Z rows, out rows)
     int ngroups;
     long long fc;               // bins per chunk
@@ -471,6 +482,8 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
     }
     if (form == 1 && s->Cd > 64) return SFA_ERR_UNSUPPORTED;
     p->form = form;
+    p->fused = (form == 1 && c64 && pwd_fused_supported(s->L, s->Q, s->T, s->Cd, p->Old, nullptr)) ? 1 : 0;
+    p->off_G2 = p->off_Xs = 0;
     // bins per chunk: keep the per-chunk scratch around `budget` bytes and the task count a
     // multiple of the SM count (tasks = bins * ceil(T/128)) so persistent CTAs finish together.
     const double budget = options().pwd_chunk_mb * 1024 * 1024;   // per slab
@@ -481,13 +494,23 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
     if (fc >= base) fc = fc / base * base;
     if (fc < 1) fc = 1;
     if (fc > s->F) fc = s->F > 0 ? s->F : 1;
+    if (p->fused) fc = s->F > 0 ? s->F : 1;     // one launch covers every bin
     p->fc = fc;
     size_t off = 0;
     p->off_G = p->off_A = p->off_dF = p->off_P1 = p->off_P2 = p->off_dcols = p->off_Z = p->a_slab = 0;
     p->off_scratch = p->scratch_bytes = 0;
     const size_t esz = c64 ? 8 : 16;
     p->off_YQt = 0;
-    if (form == 1) {
+    if (p->fused) {
+        p->off_YQt = off;
+        off += align_up((size_t)s->M * s->Q * 16);
+        p->off_G2 = off;                                      // group products in the builders' layout
+        off += align_up(pwd_fused_g2_bytes(s->L, s->Q, s->Cd));
+        p->off_dF = off;
+        off += align_up((size_t)fc * s->Cd * 8);
+        p->off_Xs = off;                                      // pre-split spectra [fc][4][T][Kp]
+        off += align_up(pwd_fused_xs_bytes(fc, s->Q, s->T));
+    } else if (form == 1) {
         p->off_YQt = off;                                     // conj(Y_Q)^T for the group products
         off += align_up((size_t)s->M * s->Q * 16);
         p->off_G = off;
@@ -544,6 +567,13 @@ static int pwd_prepare(const sfa_pwd_shape* s, const Plan& p, const double2* yl,
     const int M = s->M, Cd = s->Cd;
     const bool c64 = is_c64(s);
     const long long LQ = L * p.Qp;
+    if (p.fused) {
+        double2* yqt = reinterpret_cast<double2*>(w + p.off_YQt);
+        conj_transpose_kernel<<<grid1d(Q * M), 256, 0, st>>>(yq, Q, M, yqt);
+        SFA_LAUNCH_CHECK();
+        return launch_group_products_g2(yl, yqt, L, Q, M, Cd, s->d_is_per_order,
+                                        reinterpret_cast<float*>(w + p.off_G2), st);
+    }
     if (p.form == 1) {
         double2* yqt = reinterpret_cast<double2*>(w + p.off_YQt);
         conj_transpose_kernel<<<grid1d(Q * M), 256, 0, st>>>(yq, Q, M, yqt);
@@ -582,6 +612,14 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
     if (c64) {
         const float2* x = reinterpret_cast<const float2*>(X);
         float2* o = reinterpret_cast<float2*>(out);
+        if (p.fused) {
+            if (((uintptr_t)out) & 15) return SFA_ERR_INVALID;
+            float2* dF = reinterpret_cast<float2*>(w + p.off_dF);
+            d_to_float_kernel<<<grid1d(nf * Cd), 256, 0, st>>>(dd, nf * Cd, dF);
+            SFA_LAUNCH_CHECK();
+            return launch_pwd_fused(nf, L, Q, T, Cd, reinterpret_cast<const float*>(w + p.off_G2), dF, x,
+                                    reinterpret_cast<float*>(w + p.off_Xs), o, p.Old, is_hybrid(s), st);
+        }
         if (p.form == 1) {
             const float2* G = reinterpret_cast<const float2*>(w + p.off_G);
             float* A = reinterpret_cast<float*>(w + p.off_A);
@@ -721,7 +759,7 @@ extern "C" int sfa_pwd_apply(const sfa_pwd_shape* s, const sfa_c128* Y_L, const 
     rc = pwd_prepare(s, p, yl, reinterpret_cast<const double2*>(Y_Q), w, st);
     if (rc != SFA_OK) return rc;
     const size_t eb = elem_bytes(s);
-    if (is_c64(s) && p.form == 1 && s->F > p.fc)
+    if (is_c64(s) && p.form == 1 && !p.fused && s->F > p.fc)
         return pwd_steering_pipelined(s, p, dd, reinterpret_cast<const float2*>(X), reinterpret_cast<float2*>(out), w, st);
     for (long long f0 = 0; f0 < s->F; f0 += p.fc) {
         const long long nf = (s->F - f0 < p.fc) ? (s->F - f0) : p.fc;
@@ -761,7 +799,9 @@ extern "C" int sfa_pwd_host_create(sfa_pwd_host_ctx** out_ctx, const sfa_pwd_sha
         return rc;
     }
     c->device = device;
-    long long chunk = chunk_bins > 0 ? chunk_bins : c->plan.fc;
+    // fused steering plans cover every bin with one launch: the host pipeline still moves 74-bin chunks so
+    // that H2D, compute and D2H overlap
+    long long chunk = chunk_bins > 0 ? chunk_bins : (c->plan.fused ? 74 : c->plan.fc);
     if (chunk > s->F) chunk = s->F > 0 ? s->F : 1;
     c->chunk = chunk;
     c->operators_set = false;

@@ -1,0 +1,625 @@
+// Stage 3, steering form, in ONE persistent launch per step (sm_100a):
+//
+//     q_f = A_f X_f,   A_f = Y_L diag(d_f) Y_Q^H = sum_g d_f[g] G_g      for every frequency bin f
+//
+// i.e. the example idiom  A = matmul(matmul(Y_q, D), conj(Y_p.T)); q = matmul(A, p)
+// (doc/examples/modal_beamforming_rigid_spherical_array.py:36-39, radial.diagonal_mode_mat
+// micarray/modal/radial.py:269-314) with the [F, L, Q] steering tensor A NEVER written to memory.
+//
+// Round 1 built A_f into HBM slabs with one kernel and multiplied with another (cgemm3x_sm100.cu):
+// 2.7 GB written + ~3 GB read back per step on the headline config, a 34 us window per 74-bin slab in which
+// the GEMM could not run, and an output tile pattern (64 look directions x 128 frames per CTA) that HBM
+// absorbs at 4.9 TB/s.  Here the roles of the two GEMM operands are swapped:
+//
+//   * TMEM lanes (UMMA M = 128) = 128 look directions l of one bin.  The steering tile A_f[128 l x K<=64 mics]
+//     is the A operand IN TENSOR MEMORY (TS-form tcgen05.mma).  Eight "builder" warps compute it from the
+//     group products G (shared by all bins, L2 resident, stored so that a warp's load is 512 contiguous
+//     bytes) and the bin's radial filters d_f with FP32 FMAs in registers, split it (tf32 hi + lo / packed
+//     bf16) and write the four operand planes with tcgen05.st.  The tile of task i+1 is accumulated in
+//     registers while the MMAs of task i run; only the split + tcgen05.st (a few hundred cycles per ~40k
+//     cycle task) waits for the operand columns to be free.
+//   * UMMA N = 64 frames per step.  The spectra are pre-split once per step into the K-major planes the
+//     tensor core reads (Xs[f][plane][t][q], `x_split_kernel`: 0.5 GB in, 1 GB out) and streamed by TMA
+//     (SWIZZLE_128B, mbarrier complete_tx) into a 2-stage shared-memory ring.  The two CTAs of a cluster
+//     work on two l-tiles of the SAME bin and share that stream: each fetches half of the boxes and
+//     multicasts them.
+//   * One elected thread issues the tcgen05.mma stream (2 passes hybrid / 3 passes 3xTF32 x 4 real products
+//     x K/8 k-steps) into double-buffered (Re, Im) accumulators.
+//   * Four epilogue warps read the accumulators (lane = look direction, columns = frames), transpose them
+//     through warp-private SWIZZLE_128B staging boxes in shared memory (conflict-free 16-byte stores) and
+//     write them with TMA stores.  A CTA owns 128 consecutive rows of out[f] for ALL frames, i.e. over a
+//     task it writes one contiguous ~1 MB region of the beam tensor front to back.
+//
+// TMEM: 2 x (64 Re + 64 Im) accumulator columns + 4 x 64 operand columns = 512.
+// SMEM: 2 x 64 KB operand stages + 4 x 16 KB store staging.
+#include <cuda.h>
+#include "sfa_common.cuh"
+#include "sfa_tcgen05.cuh"
+
+namespace sfa {
+namespace fused {
+
+constexpr int kTileL = 128;                         // look directions per task (TMEM lanes)
+constexpr int kTileT = 64;                          // frames per MMA step
+constexpr int kMaxK = 64;                           // microphones (complex k) resident in TMEM
+constexpr int kStages = 2;
+constexpr int kBoxK = 32;                           // fp32 per 128-byte swizzle row
+constexpr int kBoxBytes = kTileT * kBoxK * 4;       // 8 KB
+constexpr int kStageBytes = 4 * 2 * kBoxBytes;      // 4 planes x 2 k-boxes = 64 KB
+constexpr int kEpiWarp0 = 2, kEpiWarps = 4;
+constexpr int kBuildWarp0 = 6, kBuildWarps = 8;
+constexpr int kThreads = 32 * (2 + kEpiWarps + kBuildWarps);   // 448
+constexpr int kTmemCols = 512;
+constexpr int kAccCols = 2 * kTileT;                // Re + Im per accumulator stage
+constexpr int kOperandCol0 = 2 * kAccCols;          // 256
+constexpr int kStoreBoxBytes = 32 * 128;            // 32 rows x 16 frames (128 B): one SWIZZLE_128B store box
+constexpr int kStoreWarpBytes = 4 * kStoreBoxBytes; // per epilogue warp: 2 passes x 2 boxes (double-buffered)
+
+struct Params {
+    long long F, L, T;
+    int K;                       // microphones (<= 64)
+    int ksteps, kboxes;          // ceil(K/8), ceil(K/32)
+    int ngroups;                 // columns of d (<= NG)
+    const float4* G2;            // [ltiles][ngroups][Kh][128] : (G[g][l][2j], G[g][l][2j+1]) per lane l
+    int Kh;                      // ksteps * 4 column pairs
+    const float2* d;             // [F][ngroups] complex64
+    int ltiles, lt_groups, csize, t_tiles;
+    long long groups;            // F * lt_groups
+};
+
+struct __align__(8) Barriers {
+    uint64_t b_full[kStages];
+    uint64_t b_empty[kStages];
+    uint64_t acc_full[2];
+    uint64_t acc_empty[2];
+    uint64_t a_full;
+    uint64_t a_empty;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+template <bool kHybrid, int NG>
+__global__ void __launch_bounds__(kThreads, 1)
+pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap o_map,
+                 const Params prm) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* stage_base = smem;                                   // kStages x 64 KB
+    unsigned char* store_base = smem + (size_t)kStages * kStageBytes;   // 4 x 16 KB
+    Barriers* bars = reinterpret_cast<Barriers*>(store_base + kEpiWarps * kStoreWarpBytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int csize = prm.csize;
+    const uint32_t crank = (csize > 1) ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+    const long long cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bars->b_full[s], 1);
+            mbar_init(&bars->b_empty[s], csize);        // the MMA issuer of every CTA in the cluster
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bars->acc_full[a], 1);
+            mbar_init(&bars->acc_empty[a], kEpiWarps);
+        }
+        mbar_init(&bars->a_full, kBuildWarps);
+        mbar_init(&bars->a_empty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&bars->tmem_base)),
+                     "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (csize > 1) cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    // group -> (bin f, l-tile of this CTA); a "ghost" l-tile beyond ltiles only keeps the multicast protocol alive
+    auto decode = [&](long long grp, long long& f, int& lt) {
+        f = grp / prm.lt_groups;
+        lt = (int)(grp - f * prm.lt_groups) * csize + (int)crank;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer: stream the pre-split spectra of the bin =====================
+        if (elect_one_sync()) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&x_map) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
+                const int f = (int)(grp / prm.lt_groups);
+                for (int tt = 0; tt < prm.t_tiles; ++tt) {
+                    mbar_wait(&bars->b_empty[stage], phase ^ 1);
+                    unsigned char* dst = stage_base + (size_t)stage * kStageBytes;
+                    mbar_arrive_expect_tx(&bars->b_full[stage], (uint32_t)(4 * prm.kboxes * kBoxBytes));
+#pragma unroll
+                    for (int pl = 0; pl < 4; ++pl) {
+#pragma unroll
+                        for (int kb = 0; kb < 2; ++kb) {
+                            if (kb >= prm.kboxes) continue;
+                            unsigned char* dbox = dst + (pl * 2 + kb) * kBoxBytes;
+                            if (csize == 1) {
+                                tma_load_3d(&x_map, &bars->b_full[stage], dbox, kb * kBoxK, tt * kTileT, f * 4 + pl);
+                            } else if (((prm.kboxes > 1 ? pl * 2 + kb : pl) & 1) == (int)crank) {
+                                tma_load_3d_mc(&x_map, &bars->b_full[stage], dbox, kb * kBoxK, tt * kTileT, f * 4 + pl, cmask);
+                            }
+                        }
+                    }
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const int t_tail = (int)(prm.T - (long long)(prm.t_tiles - 1) * kTileT);
+        const int t_tail16 = ((t_tail + 15) >> 4) << 4;
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+        for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
+            long long f;
+            int lt;
+            decode(grp, f, lt);
+            if (lt >= prm.ltiles) {
+                // ghost tile: consume the multicast stream, compute nothing
+                for (int tt = 0; tt < prm.t_tiles; ++tt) {
+                    mbar_wait(&bars->b_full[stage], phase);
+                    if (elect_one_sync()) tcgen05_commit_mc(&bars->b_empty[stage], cmask);
+                    __syncwarp();
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                continue;
+            }
+            mbar_wait(&bars->a_full, a_phase);
+            for (int tt = 0; tt < prm.t_tiles; ++tt) {
+                mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+                mbar_wait(&bars->b_full[stage], phase);
+                tcgen05_fence_after();
+                const int n_mma = (tt == prm.t_tiles - 1) ? t_tail16 : kTileT;
+                const uint32_t idesc = make_idesc(kTileL, n_mma, false);
+                const uint32_t idesc_neg = make_idesc(kTileL, n_mma, true);
+                const uint32_t idesc_bf = make_idesc(kTileL, n_mma, false, true);
+                const uint32_t idesc_bf_neg = make_idesc(kTileL, n_mma, true, true);
+                if (elect_one_sync()) {
+                    const uint32_t sbase = smem_u32(stage_base + (size_t)stage * kStageBytes);
+                    const uint64_t bdesc = make_b_desc(sbase);
+                    const uint32_t d_re = tmem + acc * kAccCols;
+                    const uint32_t d_im = d_re + kTileT;
+                    const uint32_t a0 = tmem + kOperandCol0;
+                    constexpr int kPasses = kHybrid ? 2 : 3;
+#pragma unroll
+                    for (int pass = 0; pass < kPasses; ++pass) {
+                        // planes {re_hi, im_hi, re_x, im_x}; x = lo (fp32) or packed bf16 pairs.
+                        // 3xTF32: (A, B) = (hi, hi) (hi, lo) (lo, hi).  hybrid: tf32 (hi, hi), then bf16 (x, x).
+                        const int ap = kHybrid ? (pass == 1 ? 2 : 0) : ((pass == 2) ? 2 : 0);
+                        const int bp = kHybrid ? (pass == 1 ? 2 : 0) : ((pass == 1) ? 2 : 0);
+                        const bool bf = kHybrid && pass == 1;
+#pragma unroll
+                        for (int ks = 0; ks < kMaxK / 8; ++ks) {
+                            if (ks < prm.ksteps) {
+                                const int kb = ks >> 2, kk = ks & 3;
+                                const uint64_t b_re = bdesc + (uint64_t)((((bp + 0) * 2 + kb) * kBoxBytes + kk * 32) >> 4);
+                                const uint64_t b_im = bdesc + (uint64_t)((((bp + 1) * 2 + kb) * kBoxBytes + kk * 32) >> 4);
+                                const uint32_t a_re = a0 + (ap + 0) * kMaxK + ks * 8;
+                                const uint32_t a_im = a0 + (ap + 1) * kMaxK + ks * 8;
+                                const uint32_t accum = (pass == 0 && ks == 0) ? 0u : 1u;
+                                if (bf) {
+                                    umma_bf16_ts(d_re, a_re, b_re, idesc_bf, accum);
+                                    umma_bf16_ts(d_re, a_im, b_im, idesc_bf_neg, 1u);
+                                    umma_bf16_ts(d_im, a_re, b_im, idesc_bf, accum);
+                                    umma_bf16_ts(d_im, a_im, b_re, idesc_bf, 1u);
+                                } else {
+                                    umma_tf32_ts(d_re, a_re, b_re, idesc, accum);
+                                    umma_tf32_ts(d_re, a_im, b_im, idesc_neg, 1u);
+                                    umma_tf32_ts(d_im, a_re, b_im, idesc, accum);
+                                    umma_tf32_ts(d_im, a_im, b_re, idesc, 1u);
+                                }
+                            }
+                        }
+                    }
+                    if (csize == 1) tcgen05_commit(&bars->b_empty[stage]);
+                    else tcgen05_commit_mc(&bars->b_empty[stage], cmask);
+                    tcgen05_commit(&bars->acc_full[acc]);
+                    if (tt == prm.t_tiles - 1) tcgen05_commit(&bars->a_empty);
+                }
+                __syncwarp();
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+            a_phase ^= 1;
+        }
+    } else if (warp >= kBuildWarp0) {
+        // ===================== builders: A_f tile = sum_g d_f[g] G_g  ->  registers -> TMEM =====================
+        // warp (quarter, half): rows quarter*32 + lane of the l-tile, mic columns [half*32, half*32 + 32)
+        const int quarter = warp & 3;
+        const int half = (warp - kBuildWarp0) >> 2;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        const int row = quarter * 32 + lane;
+        // column pairs this warp owns that actually exist (Kh = ksteps * 4 pairs; pairs beyond it stay zero)
+        int npairs = prm.Kh - half * 16;
+        npairs = npairs < 0 ? 0 : (npairs > 16 ? 16 : npairs);
+        uint32_t a_phase = 0;
+        for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
+            long long f;
+            int lt;
+            decode(grp, f, lt);
+            if (lt >= prm.ltiles) continue;
+            float2 dg[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+                dg[g] = (g < prm.ngroups) ? __ldg(prm.d + f * prm.ngroups + g) : make_float2(0.f, 0.f);
+            float are[32], aim[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) are[j] = aim[j] = 0.f;
+            const float4* gp = prm.G2 + ((size_t)lt * prm.ngroups * prm.Kh + (size_t)half * 16) * kTileL + row;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                if (g < prm.ngroups) {
+                    const float4* gg = gp + (size_t)g * prm.Kh * kTileL;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j < npairs) {
+                            const float4 v = __ldg(gg + (size_t)j * kTileL);
+                            are[2 * j] = fmaf(dg[g].x, v.x, are[2 * j]);
+                            are[2 * j] = fmaf(-dg[g].y, v.y, are[2 * j]);
+                            aim[2 * j] = fmaf(dg[g].x, v.y, aim[2 * j]);
+                            aim[2 * j] = fmaf(dg[g].y, v.x, aim[2 * j]);
+                            are[2 * j + 1] = fmaf(dg[g].x, v.z, are[2 * j + 1]);
+                            are[2 * j + 1] = fmaf(-dg[g].y, v.w, are[2 * j + 1]);
+                            aim[2 * j + 1] = fmaf(dg[g].x, v.w, aim[2 * j + 1]);
+                            aim[2 * j + 1] = fmaf(dg[g].y, v.z, aim[2 * j + 1]);
+                        }
+                    }
+                }
+            }
+            // the MMAs of the previous task must have finished reading the operand columns
+            mbar_wait(&bars->a_empty, a_phase ^ 1);
+            tcgen05_fence_after();
+            const uint32_t col = tmem + lane_base + kOperandCol0 + half * 32;
+            uint32_t w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = to_tf32(are[j]);
+            SFA_TMEM_ST32(col + 0 * kMaxK, w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float h = __uint_as_float(to_tf32(are[j]));
+                w[j] = kHybrid ? pack_bf16(h, are[j] - h) : __float_as_uint(are[j] - h);     // A side: (hi, lo)
+            }
+            SFA_TMEM_ST32(col + 2 * kMaxK, w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = to_tf32(aim[j]);
+            SFA_TMEM_ST32(col + 1 * kMaxK, w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float h = __uint_as_float(to_tf32(aim[j]));
+                w[j] = kHybrid ? pack_bf16(h, aim[j] - h) : __float_as_uint(aim[j] - h);
+            }
+            SFA_TMEM_ST32(col + 3 * kMaxK, w);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->a_full);
+            a_phase ^= 1;
+        }
+    } else {
+        // ===================== epilogue: TMEM -> regs -> swizzled smem boxes -> TMA store =====================
+        // warp owns TMEM lane quarter (warp & 3) = 32 look directions; per frame tile two passes of 32 frames.
+        const int quarter = warp & 3;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        unsigned char* const my_store = store_base + (size_t)(warp - kEpiWarp0) * kStoreWarpBytes;
+        // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+        const uint32_t row_off = (uint32_t)lane * 128u;
+        const uint32_t sw = (uint32_t)(lane & 7);
+        int acc = 0, buf = 0;
+        uint32_t acc_phase = 0;
+        for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
+            long long f;
+            int lt;
+            decode(grp, f, lt);
+            if (lt >= prm.ltiles) continue;
+            const int l0 = lt * kTileL + quarter * 32;
+            for (int tt = 0; tt < prm.t_tiles; ++tt) {
+                mbar_wait(&bars->acc_full[acc], acc_phase);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    const uint32_t t_re = tmem + lane_base + acc * kAccCols + pass * 32;
+                    uint32_t re[32], im[32];
+                    SFA_TMEM_LD32(t_re, re);
+                    SFA_TMEM_LD32(t_re + kTileT, im);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (pass == 1) {
+                        // the whole accumulator of this warp's lanes is in registers: release it
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+                    }
+                    const long long t0 = (long long)tt * kTileT + pass * 32;
+                    if (t0 >= prm.T || l0 >= prm.L) continue;                   // warp-uniform
+                    unsigned char* const sbuf = my_store + (size_t)buf * 2 * kStoreBoxBytes;
+                    // the stores issued from this buffer two passes ago must have finished reading it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        unsigned char* const box = sbuf + b * kStoreBoxBytes + row_off;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int j = 16 * b + 2 * c;
+                            *reinterpret_cast<float4*>(box + (((uint32_t)c ^ sw) << 4)) =
+                                make_float4(__uint_as_float(re[j]), __uint_as_float(im[j]),
+                                            __uint_as_float(re[j + 1]), __uint_as_float(im[j + 1]));
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&o_map, sbuf, (int)(2 * t0), l0, (int)f, false);
+                        if (t0 + 16 < prm.T)
+                            tma_store_3d(&o_map, sbuf + kStoreBoxBytes, (int)(2 * (t0 + 16)), l0, (int)f, false);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    buf ^= 1;
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    }
+
+    // outstanding bulk stores of this thread (epilogue issuers) must complete before the CTA exits
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    tcgen05_fence_before();
+    __syncthreads();
+    if (csize > 1) cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+    }
+}
+
+// X[f][q][t] complex64 -> Xs[f][4 planes][t][Kp] fp32, K-major (mic index contiguous), split for the B side of
+// the MMA: planes (re_hi, im_hi, re_x, im_x), x = lo (3xTF32) or packed bf16 (lo, hi) (hybrid).  32 x 32 tile
+// transpose through shared memory: reads coalesced along t, writes coalesced along q.
+__global__ void __launch_bounds__(256)
+x_split_kernel(const float2* __restrict__ X, long long F, int Q, long long T, int Kp, int hybrid,
+               float* __restrict__ Xs) {
+    __shared__ float2 tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const long long t_tiles = (T + 31) / 32;
+    const int q_tiles = (Kp + 31) / 32;
+    const long long tiles = F * t_tiles * q_tiles;
+    for (long long tile_id = blockIdx.x; tile_id < tiles; tile_id += gridDim.x) {
+        const long long f = tile_id / (t_tiles * q_tiles);
+        const long long r = tile_id - f * t_tiles * q_tiles;
+        const int qt = (int)(r / t_tiles);
+        const long long tt = r - (long long)qt * t_tiles;
+        const long long t0 = tt * 32;
+        const int q0 = qt * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int q = q0 + ty + 8 * i;
+            const long long t = t0 + tx;
+            tile[ty + 8 * i][tx] = (q < Q && t < T) ? __ldg(X + (f * Q + q) * T + t) : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+        const long long plane = T * Kp;
+        float* base = Xs + f * 4 * plane;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long t = t0 + ty + 8 * i;
+            const int q = q0 + tx;
+            if (t < T && q < Kp) {
+                const float2 v = tile[tx][ty + 8 * i];
+                const float hr = __uint_as_float(to_tf32(v.x)), hi = __uint_as_float(to_tf32(v.y));
+                float xr = v.x - hr, xi = v.y - hi;
+                if (hybrid) {                                          // B side: (lo, hi) = (even, odd) bf16 k
+                    xr = __uint_as_float(pack_bf16(xr, hr));
+                    xi = __uint_as_float(pack_bf16(xi, hi));
+                }
+                float* o = base + t * Kp + q;
+                o[0] = hr;
+                o[plane] = hi;
+                o[2 * plane] = xr;
+                o[3 * plane] = xi;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ int order_of_col(int i) {     // radial.repeat_n_m: column i -> order n
+    int n = (int)sqrtf((float)i);
+    while ((n + 1) * (n + 1) <= i) ++n;
+    while (n * n > i) --n;
+    return n;
+}
+
+// Group products in the builders' layout (FP64 accumulate, stored as float):
+//   G2[lt][g][j][lane] = (G_g[l][2j], G_g[l][2j+1]),  l = lt*128 + lane,  G_g[l][q] = sum_{m in g} Y_L[l,m] conj(Y_Q[q,m])
+// YQt = conj(Y_Q)^T [M][Q].  Rows l >= L and columns q >= Q are zero.
+__global__ void group_products_g2_kernel(const double2* __restrict__ YL, const double2* __restrict__ YQt, long long L,
+                                         int Q, int M, int G, int per_order, int Kh, long long total,
+                                         float4* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(i & (kTileL - 1));
+        long long r = i >> 7;
+        const int j = (int)(r % Kh);
+        r /= Kh;
+        const int g = (int)(r % G);
+        const long long lt = r / G;
+        const long long l = lt * kTileL + lane;
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        if (l < L) {
+            const int m0 = per_order ? g * g : g;
+            const int m1 = per_order ? (g + 1) * (g + 1) : g + 1;
+            for (int m = m0; m < m1 && m < M; ++m) {
+                const double2 a = YL[l * M + m];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int q = 2 * j + e;
+                    if (q < Q) {
+                        const double2 b = YQt[(long long)m * Q + q];
+                        s[2 * e] += a.x * b.x - a.y * b.y;
+                        s[2 * e + 1] += a.y * b.x + a.x * b.y;
+                    }
+                }
+            }
+        }
+        out[i] = make_float4((float)s[0], (float)s[1], (float)s[2], (float)s[3]);
+    }
+}
+
+}  // namespace fused
+
+// ------------------------------------------------------------------ host side
+bool pwd_fused_supported(long long L, long long Q, long long T, int Cd, long long out_ld, const void* out) {
+    (void)L;
+    return !options().no_fused && Q >= 1 && Q <= fused::kMaxK && Cd >= 1 && Cd <= 16 && T >= 1 &&
+           (out_ld & 1) == 0 && (((uintptr_t)out) & 15) == 0;
+}
+
+// bytes of the builders' group-product table and of the pre-split spectra of `nf` bins
+size_t pwd_fused_g2_bytes(long long L, long long Q, int Cd) {
+    const long long ltiles = ceil_div(L, fused::kTileL);
+    const long long Kh = ceil_div(Q, 8) * 4;
+    return (size_t)ltiles * Cd * Kh * fused::kTileL * sizeof(float4);
+}
+size_t pwd_fused_xs_bytes(long long nf, long long Q, long long T) {
+    const long long Kp = ceil_div(Q, 4) * 4;
+    return (size_t)nf * 4 * T * Kp * sizeof(float);
+}
+
+int launch_group_products_g2(const double2* YL, const double2* YQt, long long L, long long Q, int M, int Cd,
+                             int per_order, float* G2, cudaStream_t st) {
+    const long long ltiles = ceil_div(L, fused::kTileL);
+    const int Kh = (int)ceil_div(Q, 8) * 4;
+    const long long total = ltiles * Cd * Kh * fused::kTileL;
+    long long blocks = ceil_div(total, 256);
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    fused::group_products_g2_kernel<<<(unsigned)blocks, 256, 0, st>>>(YL, YQt, L, (int)Q, M, Cd, per_order, Kh, total,
+                                                                      reinterpret_cast<float4*>(G2));
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+// q[f] = (sum_g d[f][g] G_g) X[f] for nf bins.  d: complex64 [nf][Cd]; X: [nf][Q][T]; out: [nf][L][ldo].
+int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd, const float* G2, const float2* d,
+                     const float2* X, float* Xs, float2* out, long long ldo, int hybrid, cudaStream_t st) {
+    using namespace fused;
+    if (nf <= 0) return SFA_OK;
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) return SFA_ERR_UNSUPPORTED;
+    const int Kp = (int)ceil_div(Q, 4) * 4;
+    {
+        const long long tiles = nf * ceil_div(T, 32) * ceil_div(Kp, 32);
+        long long blocks = tiles;
+        const long long cap = (long long)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        prof_aux_begin(st);
+        x_split_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, nf, (int)Q, T, Kp, hybrid, Xs);
+        prof_aux_end(st);
+        SFA_LAUNCH_CHECK();
+    }
+    CUtensorMap xmap, omap;
+    {
+        cuuint64_t gdim[3] = {(cuuint64_t)Q, (cuuint64_t)T, (cuuint64_t)(4 * nf)};
+        cuuint64_t gstr[2] = {(cuuint64_t)Kp * 4, (cuuint64_t)T * Kp * 4};
+        cuuint32_t box[3] = {(cuuint32_t)kBoxK, (cuuint32_t)kTileT, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)Xs, gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_last_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(Xs)");
+            return SFA_ERR_CUDA;
+        }
+        // beams as fp32 [nf][L][2*ldo]; store box = 32 rows x 32 fp32 (16 frames), SWIZZLE_128B staging
+        cuuint64_t odim[3] = {(cuuint64_t)(2 * T), (cuuint64_t)L, (cuuint64_t)nf};
+        cuuint64_t ostr[2] = {(cuuint64_t)ldo * 8, (cuuint64_t)L * ldo * 8};
+        cuuint32_t obox[3] = {32, 32, 1};
+        r = encode(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)out, odim, ostr, obox, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_last_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(beams)");
+            return SFA_ERR_CUDA;
+        }
+    }
+    Params prm;
+    prm.F = nf;
+    prm.L = L;
+    prm.T = T;
+    prm.K = (int)Q;
+    prm.ksteps = (int)ceil_div(Q, 8);
+    prm.kboxes = (int)ceil_div(Q, kBoxK);
+    prm.ngroups = Cd;
+    prm.G2 = reinterpret_cast<const float4*>(G2);
+    prm.Kh = prm.ksteps * 4;
+    prm.d = d;
+    prm.ltiles = (int)ceil_div(L, kTileL);
+    prm.csize = (prm.ltiles >= 2 && !options().no_cluster) ? 2 : 1;
+    prm.lt_groups = (prm.ltiles + prm.csize - 1) / prm.csize;
+    prm.t_tiles = (int)ceil_div(T, kTileT);
+    prm.groups = nf * prm.lt_groups;
+    const size_t smem = (size_t)kStages * kStageBytes + kEpiWarps * kStoreWarpBytes + sizeof(Barriers) + 1024;
+    const long long max_clusters = sm_count() / prm.csize;
+    const long long grid = (prm.groups < max_clusters ? prm.groups : max_clusters) * prm.csize;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = prm.csize;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaError_t le;
+#define SFA_FUSED_LAUNCH(HYB, NGV)                                                      \
+    do {                                                                                \
+        SFA_ENSURE_DYN_SMEM((pwd_fused_kernel<HYB, NGV>), smem);                        \
+        prof_begin(st);                                                                 \
+        le = cudaLaunchKernelEx(&cfg, pwd_fused_kernel<HYB, NGV>, xmap, omap, prm);     \
+        prof_end(st);                                                                   \
+    } while (0)
+    if (Cd <= 9) {
+        if (hybrid) SFA_FUSED_LAUNCH(true, 9);
+        else SFA_FUSED_LAUNCH(false, 9);
+    } else {
+        if (hybrid) SFA_FUSED_LAUNCH(true, 16);
+        else SFA_FUSED_LAUNCH(false, 16);
+    }
+#undef SFA_FUSED_LAUNCH
+    if (le != cudaSuccess) {
+        set_last_cuda_error(le, "cudaLaunchKernelEx(pwd_fused_kernel)");
+        return SFA_ERR_CUDA;
+    }
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+}  // namespace sfa

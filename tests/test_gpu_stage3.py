@@ -309,3 +309,48 @@ def test_pwd_degenerate(mic):
     q = S.pwd(Y_q, dn1, Y_p, p)
     ref = O.pwd_factored(cpu(Y_q), O.repeat_n_m(cpu(dn1))[None, :], cpu(Y_p), cpu(p))
     assert tuple(q.shape) == (1, 4, 1) and bin_err(cpu(q), ref) < TOL128
+
+
+@pytest.mark.parametrize("precision", ["c64", "c64_fast"])
+def test_pwd_fused_kernel_shapes(mic, precision):
+    """The fused persistent steering kernel (A_f built in tensor memory, pwd_fused_sm100.cu) against the
+    oracle and against the slab build + GEMM pipeline it replaces, on ragged shapes: fewer than 128 look
+    directions, one row more than a tile (ghost CTA of the pair), odd tile counts, frame counts around
+    the 16/32/64-frame store boxes, few microphones (k padding), per-order and per-column filters."""
+    import torch
+    from sfa_numpy_b200 import _lib
+    A, R, S = mic.modal.angular, mic.modal.radial, mic.modal.steering
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    #        N  Q   L    F   T
+    cases = [(2, 9, 5, 3, 2), (3, 16, 128, 2, 64), (3, 20, 129, 5, 70), (4, 36, 300, 7, 130), (2, 12, 700, 4, 18),
+             (5, 64, 385, 3, 200), (7, 64, 2562, 2, 90), (1, 5, 257, 9, 34), (8, 64, 130, 3, 938)]
+    for (N, Q, L, F, T) in cases:
+        az, co, w = O.fibonacci_grid(Q)
+        azl, col, _ = O.fibonacci_grid(L)
+        Yp_ref, Yq_ref = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
+        k = O.wavenumbers(64)[:F] + 0.7
+        dn_ref, _ = O.regularize(1 / O.spherical_pw(N, k, 0.042, "rigid"), 100, "Tikh")
+        X = (rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(np.complex64)
+        ref = O.pwd_factored(Yq_ref, O.repeat_n_m(dn_ref), Yp_ref, X.astype(np.complex128))
+        Xd = torch.from_numpy(X).cuda()
+        q_f = S.pwd(Yq_ref, dn_ref, Yp_ref, Xd, precision=precision, form="steering")
+        assert bin_err(cpu(q_f), ref) < TOL64, ("fused", N, Q, L, F, T, bin_err(cpu(q_f), ref))
+        try:
+            _lib.check(lib.sfa_set_option(b"no_fused", 1.0))
+            q_s = S.pwd(Yq_ref, dn_ref, Yp_ref, Xd, precision=precision, form="steering")
+        finally:
+            lib.sfa_set_option(b"no_fused", 0.0)
+        assert bin_err(cpu(q_s), ref) < TOL64
+        assert bin_err(cpu(q_f), cpu(q_s).astype(np.complex128)) < TOL64
+    # per-column filters (circular array: d has M = 2N+1 columns, every column its own group)
+    N, Q, L, F, T = 6, 13, 200, 6, 96
+    pol = np.linspace(0, 2 * np.pi, Q, endpoint=False)
+    poll = np.linspace(0, 2 * np.pi, L, endpoint=False)
+    Pp, Pq = O.cht_matrix(N, pol, np.full(Q, 1.0 / Q)), O.cht_matrix(N, poll)
+    k = O.wavenumbers(64)[:F] + 0.7
+    Dn, _ = O.regularize(1 / O.circular_pw(N, k, 0.1, "open"), 3000, "softclip")
+    X = (rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(np.complex64)
+    ref = O.pwd_factored(Pq, Dn, Pp, X.astype(np.complex128))
+    q = S.pwd(Pq, Dn, Pp, torch.from_numpy(X).cuda(), precision=precision, form="steering")
+    assert bin_err(cpu(q), ref) < TOL64
