@@ -47,6 +47,20 @@ def needs_build():
         return f.read().strip() != source_hash()
 
 
+def build_debug(verbose=False):
+    """Second build with the timing-attribution hooks compiled in (tools/ experiments only; never loaded by
+    the package unless SFA_B200_LIB points at it)."""
+    out = os.path.join(HERE, "lib", "libsfa_b200_dbg.so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-DSFA_DEBUG_HOOKS"] + os.environ.get("SFA_BUILD_DEFS", "").split() + \
+        (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libsfa_b200_dbg.so")
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB

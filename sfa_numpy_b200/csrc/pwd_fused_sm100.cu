@@ -65,6 +65,8 @@ struct Params {
     const float2* d;             // [F][ngroups] complex64
     int ltiles, lt_groups, csize, t_tiles;
     long long groups;            // F * lt_groups
+    int debug;                   // timing attribution (SFA_DEBUG_HOOKS builds only): 1 no TMA stores, 2 no build FMAs,
+                                 // 4 no staging writes, 8 no MMAs, 16 no operand loads
 };
 
 struct __align__(8) Barriers {
@@ -137,6 +139,14 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 for (int tt = 0; tt < prm.t_tiles; ++tt) {
                     mbar_wait(&bars->b_empty[stage], phase ^ 1);
                     unsigned char* dst = stage_base + (size_t)stage * kStageBytes;
+                    if (prm.debug & 16) {
+                        mbar_arrive(&bars->b_full[stage]);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&bars->b_full[stage], (uint32_t)(4 * prm.kboxes * kBoxBytes));
 #pragma unroll
                     for (int pl = 0; pl < 4; ++pl) {
@@ -207,7 +217,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         const bool bf = kHybrid && pass == 1;
 #pragma unroll
                         for (int ks = 0; ks < kMaxK / 8; ++ks) {
-                            if (ks < prm.ksteps) {
+                            if (ks < prm.ksteps && !(prm.debug & 8)) {
                                 const int kb = ks >> 2, kk = ks & 3;
                                 const uint64_t b_re = bdesc + (uint64_t)((((bp + 0) * 2 + kb) * kBoxBytes + kk * 32) >> 4);
                                 const uint64_t b_im = bdesc + (uint64_t)((((bp + 1) * 2 + kb) * kBoxBytes + kk * 32) >> 4);
@@ -271,7 +281,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             const float4* gp = prm.G2 + ((size_t)lt * prm.ngroups * prm.Kh + (size_t)half * 16) * kTileL + row;
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
-                if (g < prm.ngroups) {
+                if (g < prm.ngroups && !(prm.debug & 2)) {
                     const float4* gg = gp + (size_t)g * prm.Kh * kTileL;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -357,6 +367,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     // the stores issued from this buffer two passes ago must have finished reading it
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     __syncwarp();
+                    if (!(prm.debug & 4))
 #pragma unroll
                     for (int b = 0; b < 2; ++b) {
                         unsigned char* const box = sbuf + b * kStoreBoxBytes + row_off;
@@ -370,7 +381,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) {
+                    if (lane == 0 && !(prm.debug & 1)) {
                         tma_store_3d(&o_map, sbuf, (int)(2 * t0), l0, (int)f, false);
                         if (t0 + 16 < prm.T)
                             tma_store_3d(&o_map, sbuf + kStoreBoxBytes, (int)(2 * (t0 + 16)), l0, (int)f, false);
@@ -583,6 +594,11 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     prm.lt_groups = (prm.ltiles + prm.csize - 1) / prm.csize;
     prm.t_tiles = (int)ceil_div(T, kTileT);
     prm.groups = nf * prm.lt_groups;
+#ifdef SFA_DEBUG_HOOKS
+    prm.debug = options().fused_debug;
+#else
+    prm.debug = 0;
+#endif
     const size_t smem = (size_t)kStages * kStageBytes + kEpiWarps * kStoreWarpBytes + sizeof(Barriers) + 1024;
     const long long max_clusters = sm_count() / prm.csize;
     const long long grid = (prm.groups < max_clusters ? prm.groups : max_clusters) * prm.csize;

@@ -42,6 +42,7 @@ static Options make_options() {
     o.issuers = ((int)env_num("SFA_ISSUERS", 1.0) == 2) ? 2 : 1;
     o.old_build = env_flag("SFA_OLD_BUILD");
     o.no_fused = env_flag("SFA_NO_FUSED");
+    o.fused_debug = (int)env_num("SFA_FUSED_DEBUG", 0.0);
     return o;
 }
 static Options g_options = make_options();
@@ -186,6 +187,7 @@ static double* option_slot(const char* key, int** islot) {
     else if (!strcmp(key, "issuers")) *islot = &o.issuers;
     else if (!strcmp(key, "old_build")) *islot = &o.old_build;
     else if (!strcmp(key, "no_fused")) *islot = &o.no_fused;
+    else if (!strcmp(key, "fused_debug")) *islot = &o.fused_debug;
     return nullptr;
 }
 int sfa_set_option(const char* key, double value) {
