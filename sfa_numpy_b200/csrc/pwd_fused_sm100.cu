@@ -46,9 +46,15 @@ constexpr int kStages = 2;
 constexpr int kBoxK = 32;                           // fp32 per 128-byte swizzle row
 constexpr int kBoxBytes = kTileT * kBoxK * 4;       // 8 KB
 constexpr int kStageBytes = 4 * 2 * kBoxBytes;      // 4 planes x 2 k-boxes = 64 KB
-constexpr int kEpiWarp0 = 2, kEpiWarps = 4;
-constexpr int kBuildWarp0 = 6, kBuildWarps = 8;
-constexpr int kThreads = 32 * (2 + kEpiWarps + kBuildWarps);   // 448
+// Four warpgroups: {TMA producer, MMA issuer, 2 spare warps}, {4 epilogue warps}, {8 builder warps}.  The roles are
+// aligned to warpgroups so that the register file can be re-divided with setmaxnreg: the builders hold a
+// 64-value accumulator tile per thread PLUS a deep batch of loads in flight (the group products come from L2 at
+// ~1000 cycles under the store traffic; with the 128 registers of a 512-thread CTA the loads serialised and the
+// builders, not the tensor pipe, set the pace -- profiles/r2_b_fused_first.txt).
+constexpr int kEpiWarp0 = 4, kEpiWarps = 4;
+constexpr int kBuildWarp0 = 8, kBuildWarps = 8;
+constexpr int kThreads = 512;
+constexpr int kRegsCtl = 56, kRegsEpi = 104, kRegsBuild = 176;   // 128 * (56 + 104) + 256 * 176 = 65536
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 2 * kTileT;                // Re + Im per accumulator stage
 constexpr int kOperandCol0 = 2 * kAccCols;          // 256
@@ -128,6 +134,10 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         lt = (int)(grp - f * prm.lt_groups) * csize + (int)crank;
     };
 
+    // setmaxnreg sits INSIDE each role's branch so that it dominates that role's code only (ptxas sizes the
+    // register allocation of a region by the setmaxnreg that dominates it)
+    if (warp < kEpiWarp0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
     if (warp == 0) {
         // ===================== TMA producer: stream the pre-split spectra of the bin =====================
         if (elect_one_sync()) {
@@ -255,7 +265,9 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             }
             a_phase ^= 1;
         }
+    }
     } else if (warp >= kBuildWarp0) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsBuild));
         // ===================== builders: A_f tile = sum_g d_f[g] G_g  ->  registers -> TMEM =====================
         // warp (quarter, half): rows quarter*32 + lane of the l-tile, mic columns [half*32, half*32 + 32)
         const int quarter = warp & 3;
@@ -283,19 +295,21 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             for (int g = 0; g < NG; ++g) {
                 if (g < prm.ngroups && !(prm.debug & 2)) {
                     const float4* gg = gp + (size_t)g * prm.Kh * kTileL;
+                    // all 16 loads of the group are issued before the first FMA (memory-level parallelism)
+                    float4 v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        v[j] = (j < npairs) ? __ldg(gg + (size_t)j * kTileL) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        if (j < npairs) {
-                            const float4 v = __ldg(gg + (size_t)j * kTileL);
-                            are[2 * j] = fmaf(dg[g].x, v.x, are[2 * j]);
-                            are[2 * j] = fmaf(-dg[g].y, v.y, are[2 * j]);
-                            aim[2 * j] = fmaf(dg[g].x, v.y, aim[2 * j]);
-                            aim[2 * j] = fmaf(dg[g].y, v.x, aim[2 * j]);
-                            are[2 * j + 1] = fmaf(dg[g].x, v.z, are[2 * j + 1]);
-                            are[2 * j + 1] = fmaf(-dg[g].y, v.w, are[2 * j + 1]);
-                            aim[2 * j + 1] = fmaf(dg[g].x, v.w, aim[2 * j + 1]);
-                            aim[2 * j + 1] = fmaf(dg[g].y, v.z, aim[2 * j + 1]);
-                        }
+                        are[2 * j] = fmaf(dg[g].x, v[j].x, are[2 * j]);
+                        are[2 * j] = fmaf(-dg[g].y, v[j].y, are[2 * j]);
+                        aim[2 * j] = fmaf(dg[g].x, v[j].y, aim[2 * j]);
+                        aim[2 * j] = fmaf(dg[g].y, v[j].x, aim[2 * j]);
+                        are[2 * j + 1] = fmaf(dg[g].x, v[j].z, are[2 * j + 1]);
+                        are[2 * j + 1] = fmaf(-dg[g].y, v[j].w, are[2 * j + 1]);
+                        aim[2 * j + 1] = fmaf(dg[g].x, v[j].w, aim[2 * j + 1]);
+                        aim[2 * j + 1] = fmaf(dg[g].y, v[j].z, aim[2 * j + 1]);
                     }
                 }
             }
@@ -329,6 +343,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             a_phase ^= 1;
         }
     } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
         // ===================== epilogue: TMEM -> regs -> swizzled smem boxes -> TMA store =====================
         // warp owns TMEM lane quarter (warp & 3) = 32 look directions; per frame tile two passes of 32 frames.
         const int quarter = warp & 3;

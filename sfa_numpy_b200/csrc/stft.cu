@@ -1,0 +1,419 @@
+// Time <-> frequency ends of the path.
+//
+// Every example script of the reference ends with
+//     q_t = np.fft.fftshift(np.fft.irfft(q, axis=0), axes=0)
+// (doc/examples/modal_beamforming_rigid_spherical_array.py:40, ..._open_circular_array.py:40, ...): an inverse
+// real FFT along the FREQUENCY axis -- the outermost axis of the beam tensor q[F, L(, T)] -- followed by a
+// half-length rotation.  `sfa_irfft_axis0` does exactly that on the device; `sfa_stft` is the matching front
+// end that turns time signals into spectra X[F, Q, T] directly in the layout the steering kernels read.
+//
+// Hand-written FFT (no cuFFT on the path):
+//   * Stockham autosort radix-4 (+ one radix-2 pass for odd log2) in shared memory, ping-pong buffers,
+//     twiddles from a table computed once in FP64;
+//   * real transforms two at a time: two adjacent columns a, b share one complex FFT
+//     (z = x_a + i x_b  <->  Z[k] = X_a[k] + i X_b[k] with the Hermitian halves), which also makes the
+//     global accesses 16..64 contiguous bytes per frequency row;
+//   * lengths that are not powers of two (the examples use n = 2 (100 - 1) = 198) go through Bluestein's
+//     chirp-z identity on top of the power-of-two kernel (m >= 2n - 1), chirp angles reduced exactly
+//     (t^2 mod 2n in integers) so that large n loses no accuracy;
+//   * float for complex64 data, double for complex128 (1e-10 class parity with np.fft).
+#include <math.h>
+#include "sfa_common.cuh"
+
+namespace sfa {
+namespace fft {
+
+template <class R>
+struct cx {
+    R x, y;
+};
+template <class R>
+__device__ __forceinline__ cx<R> mk(R a, R b) {
+    cx<R> r;
+    r.x = a;
+    r.y = b;
+    return r;
+}
+template <class R>
+__device__ __forceinline__ cx<R> cmul(cx<R> a, cx<R> b) {
+    return mk<R>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+template <class R>
+__device__ __forceinline__ cx<R> cadd(cx<R> a, cx<R> b) {
+    return mk<R>(a.x + b.x, a.y + b.y);
+}
+template <class R>
+__device__ __forceinline__ cx<R> csub(cx<R> a, cx<R> b) {
+    return mk<R>(a.x - b.x, a.y - b.y);
+}
+
+constexpr int kThreads = 512;
+
+// Forward (e^{-2 pi i jk/m}) twiddle table T[i] = exp(-2 pi i * i / m), i < m, computed in FP64.
+template <class R>
+__global__ void twiddle_kernel(int m, cx<R>* __restrict__ T) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        double s, c;
+        sincospi(-2.0 * (double)i / (double)m, &s, &c);
+        T[i] = mk<R>((R)c, (R)s);
+    }
+}
+
+// In-place-looking Stockham FFT of `nseq` sequences of length m (power of two) held in shared memory:
+// data in `a` ([nseq][m]), scratch `b`; returns the buffer that holds the result.  kInverse conjugates the
+// (forward) twiddles, i.e. computes sum_k z[k] e^{+2 pi i jk/m} (unscaled).  All threads of the CTA call it.
+template <class R, bool kInverse>
+__device__ cx<R>* fft_shared(cx<R>* a, cx<R>* b, const cx<R>* __restrict__ tw, int m, int log2m, int nseq) {
+    int Ns = 1;
+    if (log2m & 1) {
+        // one radix-2 pass (Ns = 1: no twiddles)
+        const int half = m >> 1;
+        for (int w = threadIdx.x; w < nseq * half; w += blockDim.x) {
+            const int s = w / half, j = w - s * half;
+            const cx<R>* in = a + (size_t)s * m;
+            cx<R>* out = b + (size_t)s * m;
+            const cx<R> v0 = in[j], v1 = in[j + half];
+            out[2 * j] = cadd(v0, v1);
+            out[2 * j + 1] = csub(v0, v1);
+        }
+        __syncthreads();
+        cx<R>* t = a;
+        a = b;
+        b = t;
+        Ns = 2;
+    }
+    const int quarter = m >> 2;
+    for (; Ns < m; Ns <<= 2) {
+        const int tstep = m / (Ns * 4);                    // table stride: angle(k) = k * tstep
+        for (int w = threadIdx.x; w < nseq * quarter; w += blockDim.x) {
+            const int s = w / quarter, j = w - s * quarter;
+            const cx<R>* in = a + (size_t)s * m;
+            cx<R>* out = b + (size_t)s * m;
+            const int k = j & (Ns - 1);
+            cx<R> v0 = in[j], v1 = in[j + quarter], v2 = in[j + 2 * quarter], v3 = in[j + 3 * quarter];
+            if (k) {
+                cx<R> w1 = tw[k * tstep], w2 = tw[2 * k * tstep], w3 = tw[3 * k * tstep];
+                if (kInverse) {
+                    w1.y = -w1.y;
+                    w2.y = -w2.y;
+                    w3.y = -w3.y;
+                }
+                v1 = cmul(v1, w1);
+                v2 = cmul(v2, w2);
+                v3 = cmul(v3, w3);
+            }
+            const cx<R> p = cadd(v0, v2), q = csub(v0, v2), r = cadd(v1, v3), u = csub(v1, v3);
+            // forward: d = -i u ; inverse: d = +i u
+            const cx<R> d = kInverse ? mk<R>(-u.y, u.x) : mk<R>(u.y, -u.x);
+            const int j0 = ((j - k) << 2) + k;             // (j / Ns) * Ns * 4 + k
+            out[j0] = cadd(p, r);
+            out[j0 + Ns] = cadd(q, d);
+            out[j0 + 2 * Ns] = csub(p, r);
+            out[j0 + 3 * Ns] = csub(q, d);
+        }
+        __syncthreads();
+        cx<R>* t = a;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+// Bluestein tables for length n (sign +: inverse DFT): chirp[t] = exp(+i pi t^2 / n), t < n, and
+// Bf = FFT_m(bwrap), bwrap[t] = conj(chirp[|t|]) wrapped on m points.  One CTA.
+template <class R>
+__global__ void __launch_bounds__(kThreads)
+bluestein_setup_kernel(int n, int m, int log2m, int sign, const cx<R>* __restrict__ tw, cx<R>* __restrict__ chirp,
+                       cx<R>* __restrict__ Bf) {
+    extern __shared__ unsigned char smem_raw[];
+    cx<R>* a = reinterpret_cast<cx<R>*>(smem_raw);
+    cx<R>* b = a + m;
+    for (int t = threadIdx.x; t < m; t += blockDim.x) a[t] = mk<R>((R)0, (R)0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const long long t2 = ((long long)t * t) % (2LL * n);          // exact angle reduction
+        double s, c;
+        sincospi((double)sign * (double)t2 / (double)n, &s, &c);
+        chirp[t] = mk<R>((R)c, (R)s);
+        const cx<R> bc = mk<R>((R)c, (R)(-s));                         // conj(chirp)
+        a[t] = bc;
+        if (t) a[m - t] = bc;
+    }
+    __syncthreads();
+    cx<R>* res = fft_shared<R, false>(a, b, tw, m, log2m, 1);
+    for (int t = threadIdx.x; t < m; t += blockDim.x) Bf[t] = res[t];
+}
+
+struct IrfftParams {
+    long long F, C, n;            // bins available, columns, output samples
+    long long ld, ldo;            // row pitches (elements) of q and out
+    int m, log2m;                 // power-of-two FFT length (m == n: direct, else Bluestein)
+    int nseq;                     // column pairs per CTA tile
+    int shift;                    // fftshift rotation (n / 2 or 0)
+};
+
+// out[(j + shift) % n, c] = (1/n) sum_k Xh[k, c] e^{+2 pi i jk/n},  Xh = Hermitian extension of q[0 .. n/2, c]
+// (imaginary parts of the DC and -- for even n -- Nyquist bins ignored, bins >= F taken as zero: np.fft.irfft).
+template <class R>
+__global__ void __launch_bounds__(kThreads)
+irfft_axis0_kernel(const IrfftParams prm, const cx<R>* __restrict__ q, R* __restrict__ out,
+                   const cx<R>* __restrict__ tw_g, const cx<R>* __restrict__ chirp, const cx<R>* __restrict__ Bf) {
+    extern __shared__ unsigned char smem_raw[];
+    const int m = prm.m, nseq = prm.nseq;
+    const long long n = prm.n;
+    cx<R>* tw = reinterpret_cast<cx<R>*>(smem_raw);
+    cx<R>* a = tw + m;
+    cx<R>* b = a + (size_t)nseq * m;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) tw[i] = tw_g[i];
+    const bool direct = (m == n);
+    const int cols = 2 * nseq;
+    const long long tiles = (prm.C + cols - 1) / cols;
+    const long long kmax = n / 2;                       // highest bin index used
+    const R scale = (R)(1.0 / (double)n);
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long c0 = tile * cols;
+        __syncthreads();                                 // previous tile's readers of a/b are done; tw is loaded
+        // ---- zero, then load + Hermitian pack: Z[k] = Xa[k] + i Xb[k], Z[n-k] = conj(Xa[k]) + i conj(Xb[k])
+        for (int i = threadIdx.x; i < nseq * m; i += blockDim.x) a[i] = mk<R>((R)0, (R)0);
+        __syncthreads();
+        for (long long w = threadIdx.x; w < (kmax + 1) * nseq; w += blockDim.x) {
+            const long long k = w / nseq;
+            const int s = (int)(w - k * nseq);
+            const long long ca = c0 + 2 * s, cb = ca + 1;
+            cx<R> xa = mk<R>((R)0, (R)0), xb = xa;
+            if (k < prm.F) {
+                if (ca < prm.C) xa = q[k * prm.ld + ca];
+                if (cb < prm.C) xb = q[k * prm.ld + cb];
+            }
+            const bool self_conj = (k == 0) || (2 * k == n);
+            if (self_conj) {
+                xa.y = (R)0;
+                xb.y = (R)0;
+            }
+            cx<R> zk = mk<R>(xa.x - xb.y, xa.y + xb.x);                   // Xa + i Xb
+            cx<R> zn = mk<R>(xa.x + xb.y, xb.x - xa.y);                   // conj(Xa) + i conj(Xb)
+            cx<R>* seq = a + (size_t)s * m;
+            if (!direct) {                                                 // Bluestein: a[k] = Z[k] chirp[k]
+                zk = cmul(zk, chirp[k]);
+                if (!self_conj) zn = cmul(zn, chirp[n - k]);
+            }
+            seq[k] = zk;
+            if (!self_conj) seq[n - k] = zn;
+        }
+        __syncthreads();
+        cx<R>* res;
+        if (direct) {
+            res = fft_shared<R, true>(a, b, tw, m, prm.log2m, nseq);
+        } else {
+            cx<R>* fa = fft_shared<R, false>(a, b, tw, m, prm.log2m, nseq);
+            cx<R>* other = (fa == a) ? b : a;
+            for (int i = threadIdx.x; i < nseq * m; i += blockDim.x) fa[i] = cmul(fa[i], Bf[i & (m - 1)]);
+            __syncthreads();
+            res = fft_shared<R, true>(fa, other, tw, m, prm.log2m, nseq);
+        }
+        // ---- unpack: x_a[j] = Re z[j] / n, x_b[j] = Im z[j] / n (Bluestein: times chirp[j] / m first)
+        const R bscale = direct ? scale : (R)(1.0 / ((double)n * (double)m));
+        for (long long w = threadIdx.x; w < n * nseq; w += blockDim.x) {
+            const long long j = w / nseq;
+            const int s = (int)(w - j * nseq);
+            cx<R> z = res[(size_t)s * m + j];
+            if (!direct) z = cmul(z, chirp[j]);
+            long long jo = j + prm.shift;
+            if (jo >= n) jo -= n;
+            const long long ca = c0 + 2 * s;
+            R* o = out + jo * prm.ldo + ca;
+            if (ca < prm.C) o[0] = z.x * bscale;
+            if (ca + 1 < prm.C) o[1] = z.y * bscale;
+        }
+    }
+}
+
+struct StftParams {
+    long long Q, S, T;            // channels, samples per channel, frames
+    int nfft, hop, log2n;
+    long long Fk;                 // bins kept (<= nfft/2 + 1)
+    int nseq;                     // frame pairs per CTA tile
+};
+
+// X[f, q, t] = sum_j win[j] x[q, t*hop + j] e^{-2 pi i f j / nfft}   (np.fft.rfft of the windowed frame)
+template <class R>
+__global__ void __launch_bounds__(kThreads)
+stft_kernel(const StftParams prm, const R* __restrict__ x, const R* __restrict__ win, cx<R>* __restrict__ X,
+            const cx<R>* __restrict__ tw_g) {
+    extern __shared__ unsigned char smem_raw[];
+    const int n = prm.nfft, nseq = prm.nseq;
+    cx<R>* tw = reinterpret_cast<cx<R>*>(smem_raw);
+    cx<R>* a = tw + n;
+    cx<R>* b = a + (size_t)nseq * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tw[i] = tw_g[i];
+    const int frames = 2 * nseq;
+    const long long ttiles = (prm.T + frames - 1) / frames;
+    const long long tiles = prm.Q * ttiles;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long qi = tile / ttiles;
+        const long long t0 = (tile - qi * ttiles) * frames;
+        __syncthreads();
+        const R* xq = x + qi * prm.S;
+        for (int w = threadIdx.x; w < nseq * n; w += blockDim.x) {
+            const int s = w / n, j = w - s * n;
+            const long long ta = t0 + 2 * s, tb = ta + 1;
+            const R wj = win ? win[j] : (R)1;
+            const R va = (ta < prm.T) ? xq[ta * prm.hop + j] * wj : (R)0;
+            const R vb = (tb < prm.T) ? xq[tb * prm.hop + j] * wj : (R)0;
+            a[w] = mk<R>(va, vb);
+        }
+        __syncthreads();
+        cx<R>* res = fft_shared<R, false>(a, b, tw, n, prm.log2n, nseq);
+        // Xa[k] = (Z[k] + conj(Z[n-k])) / 2,  Xb[k] = (Z[k] - conj(Z[n-k])) / (2i)
+        for (long long w = threadIdx.x; w < prm.Fk * nseq; w += blockDim.x) {
+            const long long k = w / nseq;
+            const int s = (int)(w - k * nseq);
+            const cx<R>* z = res + (size_t)s * n;
+            const cx<R> zk = z[k], zn = z[(n - k) & (n - 1)];
+            const cx<R> xa = mk<R>((R)0.5 * (zk.x + zn.x), (R)0.5 * (zk.y - zn.y));
+            const cx<R> xb = mk<R>((R)0.5 * (zk.y + zn.y), (R)0.5 * (zn.x - zk.x));
+            const long long ta = t0 + 2 * s;
+            cx<R>* o = X + (k * prm.Q + qi) * prm.T + ta;
+            if (ta < prm.T) o[0] = xa;
+            if (ta + 1 < prm.T) o[1] = xb;
+        }
+    }
+}
+
+static int ilog2(long long v) {
+    int l = 0;
+    while ((1LL << l) < v) ++l;
+    return l;
+}
+
+template <class R>
+static int run_irfft(long long F, long long C, long long n, const void* q, long long ld, void* out, long long ldo,
+                     int shift, void* work, size_t work_bytes, cudaStream_t st) {
+    const bool pow2 = (n & (n - 1)) == 0;
+    const long long m = pow2 ? n : (1LL << ilog2(2 * n - 1));
+    const int log2m = ilog2(m);
+    const size_t esz = sizeof(cx<R>);
+    if (m > 16384 || m < 2) return SFA_ERR_UNSUPPORTED;
+    const size_t need = (size_t)m * esz + (pow2 ? 0 : (size_t)(n + m) * esz);
+    if (work_bytes < need || !work) return SFA_ERR_WORKSPACE;
+    cx<R>* tw = reinterpret_cast<cx<R>*>(work);
+    cx<R>* chirp = tw + m;
+    cx<R>* Bf = chirp + n;
+    twiddle_kernel<R><<<(unsigned)ceil_div(m, 256), 256, 0, st>>>((int)m, tw);
+    SFA_LAUNCH_CHECK();
+    if (!pow2) {
+        const size_t smem = 2 * (size_t)m * esz;
+        SFA_ENSURE_DYN_SMEM(bluestein_setup_kernel<R>, smem);
+        bluestein_setup_kernel<R><<<1, kThreads, smem, st>>>((int)n, (int)m, log2m, +1, tw, chirp, Bf);
+        SFA_LAUNCH_CHECK();
+    }
+    // column pairs per tile: as many as fit in ~200 KB next to the twiddle table (capped at 8 = 16 columns)
+    const size_t budget = 200 * 1024;
+    long long nseq = ((long long)budget - (long long)(m * esz)) / (long long)(2 * m * esz);
+    if (nseq < 1) return SFA_ERR_UNSUPPORTED;
+    if (nseq > 8) nseq = 8;
+    if (nseq > (C + 1) / 2) nseq = (C + 1) / 2;
+    // two resident CTAs per SM hide the barrier-heavy passes better than one fat one, when they fit
+    if (nseq >= 4 && (size_t)m * esz + (size_t)nseq * m * esz <= 100 * 1024) nseq /= 2;
+    IrfftParams prm;
+    prm.F = F;
+    prm.C = C;
+    prm.n = n;
+    prm.ld = ld;
+    prm.ldo = ldo;
+    prm.m = (int)m;
+    prm.log2m = log2m;
+    prm.nseq = (int)nseq;
+    prm.shift = shift ? (int)(n / 2) : 0;
+    const size_t smem = (size_t)m * esz + 2 * (size_t)nseq * m * esz;
+    SFA_ENSURE_DYN_SMEM(irfft_axis0_kernel<R>, smem);
+    const long long tiles = ceil_div(C, 2 * nseq);
+    const long long per_sm = (smem <= 100 * 1024) ? 2 : 1;
+    long long blocks = tiles;
+    if (blocks > sm_count() * per_sm) blocks = sm_count() * per_sm;
+    prof_begin(st);
+    irfft_axis0_kernel<R><<<(unsigned)blocks, kThreads, smem, st>>>(prm, reinterpret_cast<const cx<R>*>(q),
+                                                                    reinterpret_cast<R*>(out), tw, chirp, Bf);
+    prof_end(st);
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+template <class R>
+static int run_stft(long long Q, long long S, int nfft, int hop, long long Fk, const void* x, const void* win,
+                    void* X, void* work, size_t work_bytes, cudaStream_t st) {
+    const size_t esz = sizeof(cx<R>);
+    if (work_bytes < (size_t)nfft * esz || !work) return SFA_ERR_WORKSPACE;
+    const long long T = 1 + (S - nfft) / hop;
+    cx<R>* tw = reinterpret_cast<cx<R>*>(work);
+    twiddle_kernel<R><<<(unsigned)ceil_div(nfft, 256), 256, 0, st>>>(nfft, tw);
+    SFA_LAUNCH_CHECK();
+    const size_t budget = 200 * 1024;
+    long long nseq = ((long long)budget - (long long)(nfft * esz)) / (long long)(2 * nfft * esz);
+    if (nseq < 1) return SFA_ERR_UNSUPPORTED;
+    if (nseq > 8) nseq = 8;
+    if (nseq > (T + 1) / 2) nseq = (T + 1) / 2;
+    StftParams prm;
+    prm.Q = Q;
+    prm.S = S;
+    prm.T = T;
+    prm.nfft = nfft;
+    prm.hop = hop;
+    prm.log2n = ilog2(nfft);
+    prm.Fk = Fk;
+    prm.nseq = (int)nseq;
+    const size_t smem = (size_t)nfft * esz + 2 * (size_t)nseq * nfft * esz;
+    SFA_ENSURE_DYN_SMEM(stft_kernel<R>, smem);
+    const long long tiles = Q * ceil_div(T, 2 * nseq);
+    long long blocks = tiles;
+    const long long per_sm = (smem <= 100 * 1024) ? 2 : 1;
+    if (blocks > sm_count() * per_sm) blocks = sm_count() * per_sm;
+    stft_kernel<R><<<(unsigned)blocks, kThreads, smem, st>>>(prm, reinterpret_cast<const R*>(x),
+                                                             reinterpret_cast<const R*>(win),
+                                                             reinterpret_cast<cx<R>*>(X), tw);
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+}  // namespace fft
+}  // namespace sfa
+
+using namespace sfa;
+
+extern "C" size_t sfa_irfft_work_bytes(int64_t n, int is_double) {
+    if (n < 1) return 0;
+    const bool pow2 = (n & (n - 1)) == 0;
+    const long long m = pow2 ? n : (1LL << fft::ilog2(2 * n - 1));
+    const size_t esz = is_double ? 16 : 8;
+    return (size_t)m * esz + (pow2 ? 0 : (size_t)(n + m) * esz) + 256;
+}
+
+extern "C" int sfa_irfft_axis0(int64_t F, int64_t C, int64_t n, const void* q, int64_t ld, void* out, int64_t ldo,
+                               int is_double, int shift, void* work, size_t work_bytes, void* stream) {
+    if (F < 0 || C < 0 || n < 0 || ld < C || ldo < C) return SFA_ERR_INVALID;
+    if (n == 0) n = 2 * (F - 1);                         // np.fft.irfft default
+    if (n < 1) return SFA_ERR_INVALID;                   // numpy: "Invalid number of FFT data points"
+    if (C == 0) return SFA_OK;
+    if (!q && F > 0) return SFA_ERR_INVALID;
+    if (!out) return SFA_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 1) n = 1;
+    return is_double ? fft::run_irfft<double>(F, C, n, q, ld, out, ldo, shift, work, work_bytes, st)
+                     : fft::run_irfft<float>(F, C, n, q, ld, out, ldo, shift, work, work_bytes, st);
+}
+
+extern "C" size_t sfa_stft_work_bytes(int nfft, int is_double) {
+    return nfft > 0 ? (size_t)nfft * (is_double ? 16 : 8) + 256 : 0;
+}
+
+extern "C" int sfa_stft(int64_t Q, int64_t S, int nfft, int hop, int64_t F_keep, const void* x, const void* window,
+                        void* X, int is_double, void* work, size_t work_bytes, void* stream) {
+    if (Q < 0 || nfft < 2 || (nfft & (nfft - 1)) || nfft > 16384 || hop < 1 || S < nfft) return SFA_ERR_INVALID;
+    if (F_keep <= 0) F_keep = nfft / 2 + 1;
+    if (F_keep > nfft / 2 + 1) return SFA_ERR_INVALID;
+    if (Q == 0) return SFA_OK;
+    if (!x || !X) return SFA_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    return is_double ? fft::run_stft<double>(Q, S, nfft, hop, F_keep, x, window, X, work, work_bytes, st)
+                     : fft::run_stft<float>(Q, S, nfft, hop, F_keep, x, window, X, work, work_bytes, st);
+}

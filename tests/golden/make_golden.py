@@ -170,6 +170,7 @@ def golden_examples():
     sys.modules["matplotlib"] = mpl
     sys.modules["matplotlib.pyplot"] = plt
     out = {}
+    out_t = {}
     cwd = os.getcwd()
     os.chdir(tempfile.mkdtemp())
     try:
@@ -179,12 +180,15 @@ def golden_examples():
             with np.errstate(all="ignore"):
                 g = runpy.run_path(path)
             out[name + "_q"] = np.asarray(g[qvar])
+            # the examples' last step: q_t = fftshift(irfft(q, axis=0), axes=0)  (e.g. ..._rigid_spherical_array.py:40)
+            out_t[name + "_q_t"] = np.asarray(g[qvar + "_t"])
             if name != "open_spherical":      # closed form; rebuilt in the test (1.4 MB saved)
                 out[name + "_p"] = np.asarray(g["p"])
             out[name + "_k"] = np.asarray(g["k"], dtype=float)
     finally:
         os.chdir(cwd)
     save("examples", **out)
+    save("examples_time", **out_t)
 
 
 def golden_extras():
