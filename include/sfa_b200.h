@@ -206,6 +206,30 @@ int sfa_host_free(void* p);
  * multi-GPU path).  q: rows = F*L rows of T complex64 with row pitch ld (elements); out: [rows] float32. */
 int sfa_power_map(int64_t rows, int64_t T, int64_t ld, const sfa_c64* q, float* out, void* stream);
 
+/* ---- time <-> frequency ends of the path -------------------------------- */
+
+/* np.fft.irfft(q, n, axis=0), optionally followed by np.fft.fftshift(., axes=0): the last step of every
+ * example script, q_t = fftshift(irfft(q, axis=0), axes=0)
+ * (doc/examples/modal_beamforming_rigid_spherical_array.py:40, ..._open_circular_array.py:40).
+ *   q   [F, C] complex (C = product of the trailing axes, e.g. L or L*T; row pitch ld elements)
+ *   n   output samples; 0 = NumPy's default 2 (F - 1).  Bins beyond n/2 are ignored, missing bins are zero,
+ *       the imaginary parts of the DC (and, for even n, Nyquist) bins are ignored -- as np.fft.irfft does.
+ *   out [n, C] real (row pitch ldo): float32 for complex64 input (is_double = 0), float64 for complex128.
+ * Hand-written shared-memory FFT (radix-4 Stockham, two real columns per complex transform); any n up to
+ * 16384 (powers of two directly, other lengths through Bluestein's chirp-z identity).
+ * `work`: device scratch of sfa_irfft_work_bytes(n, is_double) bytes (twiddle / chirp tables). */
+size_t sfa_irfft_work_bytes(int64_t n, int is_double);
+int sfa_irfft_axis0(int64_t F, int64_t C, int64_t n, const void* q, int64_t ld, void* out, int64_t ldo,
+                    int is_double, int shift, void* work, size_t work_bytes, void* stream);
+
+/* STFT front end producing the spectra directly in the steering operator's layout:
+ *   X[f, q, t] = sum_j window[j] x[q, t*hop + j] exp(-2 pi i f j / nfft),  f < F_keep (0 = nfft/2 + 1),
+ *   t < T = 1 + (S - nfft) / hop; x [Q, S] real, window [nfft] real or NULL (rectangular), X [F_keep, Q, T].
+ * nfft: power of two <= 16384.  float32/complex64 (is_double = 0) or float64/complex128. */
+size_t sfa_stft_work_bytes(int nfft, int is_double);
+int sfa_stft(int64_t Q, int64_t S, int nfft, int hop, int64_t F_keep, const void* x, const void* window,
+             void* X, int is_double, void* work, size_t work_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

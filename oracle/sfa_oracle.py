@@ -412,3 +412,31 @@ def coherence_of_columns(A):
     G = An.conj().T @ An
     np.fill_diagonal(G, 0)
     return np.max(np.abs(G))
+
+
+# --------------------------------------------------------------------------- time <-> frequency ends
+def irfft_shift(q, n=None):
+    """Back end of every example script: ``np.fft.fftshift(np.fft.irfft(q, axis=0), axes=0)``
+    (doc/examples/modal_beamforming_rigid_spherical_array.py:40, ..._open_circular_array.py:40,
+    ..._open_spherical_array.py:40, ..._rigid_circular_array.py:37).  NumPy's pocketfft is the third-party
+    arithmetic here (numpy!=1.11.0, setup.py:39); `n` as in np.fft.irfft (default 2 (F - 1))."""
+    return np.fft.fftshift(np.fft.irfft(q, n=n, axis=0), axes=0)
+
+
+def irfft_axis0(q, n=None):
+    return np.fft.irfft(q, n=n, axis=0)
+
+
+def stft(x, nfft, hop, window=None, bins=None):
+    """Front end matching `sfa_stft` (the reference has none -- its examples start from spectra):
+    X[f, q, t] = rfft(window * x[q, t*hop : t*hop + nfft])[f], no padding, no scaling; [F, Q, T] layout of the
+    steering operator's input (the `p` of the examples with a frame axis)."""
+    x = np.atleast_2d(np.asarray(x))
+    Q, S = x.shape
+    T = 1 + (S - nfft) // hop
+    win = np.ones(nfft) if window is None else np.asarray(window)
+    idx = np.arange(nfft)[None, :] + hop * np.arange(T)[:, None]
+    frames = x[:, idx] * win                                  # [Q, T, nfft]
+    X = np.fft.rfft(frames, axis=2)                           # [Q, T, nfft/2+1]
+    X = np.transpose(X, (2, 0, 1))
+    return X if bins is None else X[:bins]

@@ -11,3 +11,4 @@ __version__ = "0.1.0"
 
 from . import modal
 from . import util
+from . import fft

@@ -60,6 +60,12 @@ SIGNATURES = {
     "sfa_pwd_host_run": (c_int, [c_void_p, c_void_p, c_void_p]),
     "sfa_pwd_host_destroy": (c_int, [c_void_p]),
     "sfa_power_map": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "sfa_irfft_work_bytes": (c_size_t, [c_int64, c_int]),
+    "sfa_irfft_axis0": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
+                                c_void_p, c_size_t, c_void_p]),
+    "sfa_stft_work_bytes": (c_size_t, [c_int, c_int]),
+    "sfa_stft": (c_int, [c_int64, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int,
+                         c_void_p, c_size_t, c_void_p]),
     "sfa_host_alloc": (c_int, [ctypes.POINTER(c_void_p), c_size_t]),
     "sfa_host_free": (c_int, [c_void_p]),
 }
