@@ -47,18 +47,22 @@ def needs_build():
         return f.read().strip() != source_hash()
 
 
-def build_debug(verbose=False):
-    """Second build with the timing-attribution hooks compiled in (tools/ experiments only; never loaded by
-    the package unless SFA_B200_LIB points at it)."""
-    out = os.path.join(HERE, "lib", "libsfa_b200_dbg.so")
+def build_variant(name, defs, verbose=False):
+    """Extra build of the library with additional -D flags (tools/ experiments only; never loaded by the
+    package unless SFA_B200_LIB points at it)."""
+    out = os.path.join(HERE, "lib", "libsfa_b200_%s.so" % name)
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-DSFA_DEBUG_HOOKS"] + os.environ.get("SFA_BUILD_DEFS", "").split() + \
-        (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + list(defs) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libsfa_b200_dbg.so")
+        raise RuntimeError("nvcc failed building " + out)
     return out
+
+
+def build_debug(verbose=False):
+    """Build with the timing-attribution hooks compiled in."""
+    return build_variant("dbg", ["-DSFA_DEBUG_HOOKS"], verbose)
 
 
 def build(force=False, verbose=False):

@@ -59,7 +59,11 @@ constexpr int kTmemCols = 512;
 constexpr int kAccCols = 2 * kTileT;                // Re + Im per accumulator stage
 constexpr int kOperandCol0 = 2 * kAccCols;          // 256
 constexpr int kStoreBoxBytes = 32 * 128;            // 32 rows x 16 frames (128 B): one SWIZZLE_128B store box
-constexpr int kStoreWarpBytes = 4 * kStoreBoxBytes; // per epilogue warp: 2 passes x 2 boxes (double-buffered)
+#ifndef SFA_FUSED_RING
+#define SFA_FUSED_RING 2
+#endif
+constexpr int kStoreRing = SFA_FUSED_RING;          // staging slots (one pass = 2 boxes = 8 KB each) per epilogue warp
+constexpr int kStoreWarpBytes = kStoreRing * 2 * kStoreBoxBytes;
 
 struct Params {
     long long F, L, T;
@@ -379,8 +383,8 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     const long long t0 = (long long)tt * kTileT + pass * 32;
                     if (t0 >= prm.T || l0 >= prm.L) continue;                   // warp-uniform
                     unsigned char* const sbuf = my_store + (size_t)buf * 2 * kStoreBoxBytes;
-                    // the stores issued from this buffer two passes ago must have finished reading it
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    // the stores issued from this slot kStoreRing passes ago must have finished reading it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStoreRing - 1) : "memory");
                     __syncwarp();
                     if (!(prm.debug & 4))
 #pragma unroll
@@ -402,7 +406,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                             tma_store_3d(&o_map, sbuf + kStoreBoxBytes, (int)(2 * (t0 + 16)), l0, (int)f, false);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    buf ^= 1;
+                    if (++buf == kStoreRing) buf = 0;
                 }
                 if (++acc == 2) {
                     acc = 0;

@@ -193,3 +193,14 @@ def test_extras(golden):
     assert_close(O.norm_of_columns(g["mdm_A"], 1), g["noc1"], **TIGHT)
     assert abs(O.coherence_of_columns(g["mdm_A"]) - float(g["coh"])) < 1e-14
     assert abs(O.coherence_of_columns(g["coh_Y_in"]) - float(g["coh_Y"])) < 1e-14
+
+
+def test_oracle_irfft_shift_matches_examples(golden):
+    """The examples' last step, q_t = fftshift(irfft(q, axis=0), axes=0): the oracle restatement applied to the
+    golden q of the unmodified scripts reproduces their q_t bit-exactly (same NumPy)."""
+    import os
+    gt = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "examples_time.npz"))
+    for name in ("open_circular", "rigid_circular", "open_spherical", "rigid_spherical"):
+        out = O.irfft_shift(golden["examples"][name + "_q"])
+        assert out.shape == gt[name + "_q_t"].shape == (198, golden["examples"][name + "_q"].shape[1])
+        assert np.array_equal(out, gt[name + "_q_t"])
