@@ -176,6 +176,18 @@ int sfa_pwd_apply(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* Y
                   const sfa_c128* d, const void* X, void* out, void* work, size_t work_bytes,
                   void* stream);
 
+/* The same in two steps, for operators that stay resident while spectra stream through:
+ *   sfa_pwd_prepare  everything that depends on Y_L / Y_Q only (group products G_g = sum_{m in g} Y_L[:,m] Y_Q[:,m]^H
+ *                    or the split operand planes), written into `work`;
+ *   sfa_pwd_run      q = ... for the current d and X, reading the prepared `work` (same shape, same work buffer).
+ * `power` (nullable, complex64 precisions only): additionally writes the beam power map mean_t |q[f,l,t]|^2 as
+ * float32 [F, L] (see sfa_power_map).  The fused steering kernel accumulates it in its epilogue -- a CTA owns
+ * whole rows of q -- so it costs no extra pass over the beams; other paths append one sfa_power_map pass. */
+int sfa_pwd_prepare(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* Y_Q, void* work, size_t work_bytes,
+                    void* stream);
+int sfa_pwd_run(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* d, const void* X, void* out,
+                float* power, void* work, size_t work_bytes, void* stream);
+
 /* Batched complex GEMM building block used by sfa_pwd_apply, exposed for tests:
  *   out[b, n, m] = sum_k P[b?, n, k] * R[b, k, m]  (* rowscale[b, n] if given)
  * complex64 on tcgen05, 3xTF32 (hybrid = 0) or TF32+BF16 (hybrid = 1).  ldP, ldR, ldo in elements;
@@ -215,8 +227,9 @@ int sfa_power_map(int64_t rows, int64_t T, int64_t ld, const sfa_c64* q, float* 
  *   n   output samples; 0 = NumPy's default 2 (F - 1).  Bins beyond n/2 are ignored, missing bins are zero,
  *       the imaginary parts of the DC (and, for even n, Nyquist) bins are ignored -- as np.fft.irfft does.
  *   out [n, C] real (row pitch ldo): float32 for complex64 input (is_double = 0), float64 for complex128.
- * Hand-written shared-memory FFT (radix-4 Stockham, two real columns per complex transform); any n up to
- * 16384 (powers of two directly, other lengths through Bluestein's chirp-z identity).
+ * Hand-written shared-memory FFT (radix-4 Stockham, two real columns per complex transform): powers of two
+ * n <= 8192 (float) / 4096 (double) directly, other lengths through Bluestein's chirp-z identity on the next
+ * power of two >= 2n - 1 (so n <= 4096 / 2048); beyond that SFA_ERR_UNSUPPORTED.
  * `work`: device scratch of sfa_irfft_work_bytes(n, is_double) bytes (twiddle / chirp tables). */
 size_t sfa_irfft_work_bytes(int64_t n, int is_double);
 int sfa_irfft_axis0(int64_t F, int64_t C, int64_t n, const void* q, int64_t ld, void* out, int64_t ldo,

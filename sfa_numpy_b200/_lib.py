@@ -53,6 +53,9 @@ SIGNATURES = {
     "sfa_pwd_work_bytes": (c_size_t, [ctypes.POINTER(PwdShape)]),
     "sfa_pwd_apply": (c_int, [ctypes.POINTER(PwdShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_void_p]),
+    "sfa_pwd_prepare": (c_int, [ctypes.POINTER(PwdShape), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sfa_pwd_run": (c_int, [ctypes.POINTER(PwdShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_size_t, c_void_p]),
     "sfa_cgemm3x": (c_int, [c_int64] * 4 + [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                             c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "sfa_pwd_host_create": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(PwdShape), c_int, c_int64]),

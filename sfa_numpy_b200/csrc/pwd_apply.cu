@@ -38,7 +38,8 @@ size_t pwd_fused_xs_bytes(long long nf, long long Q, long long T);
 int launch_group_products_g2(const double2* YL, const double2* YQt, long long L, long long Q, int M, int Cd,
                              int per_order, float* G2, cudaStream_t st);
 int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd, const float* G2, const float2* d,
-                     const float2* X, float* Xs, float2* out, long long ldo, int hybrid, cudaStream_t st);
+                     const float2* X, float* Xs, float2* out, long long ldo, float* power, int hybrid,
+                     cudaStream_t st);
 
 static inline bool use_kloop(long long K, int p_shared) { return K > 64 && p_shared && !options().no_kloop; }
 
@@ -603,7 +604,7 @@ static unsigned zgrid(long long tiles) { return (unsigned)(tiles < 65535LL * 16 
 
 // Bins [0, nf) of d / X / out (pointers already offset to the first bin); nf <= p.fc.
 static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, const double2* yl, const double2* dd,
-                        const void* X, void* out, unsigned char* w, cudaStream_t st) {
+                        const void* X, void* out, unsigned char* w, cudaStream_t st, float* power = nullptr) {
     const long long L = s->L, Q = s->Q, T = s->T;
     const int M = s->M, Cd = s->Cd;
     const bool c64 = is_c64(s);
@@ -618,7 +619,7 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
             d_to_float_kernel<<<grid1d(nf * Cd), 256, 0, st>>>(dd, nf * Cd, dF);
             SFA_LAUNCH_CHECK();
             return launch_pwd_fused(nf, L, Q, T, Cd, reinterpret_cast<const float*>(w + p.off_G2), dF, x,
-                                    reinterpret_cast<float*>(w + p.off_Xs), o, p.Old, is_hybrid(s), st);
+                                    reinterpret_cast<float*>(w + p.off_Xs), o, p.Old, power, is_hybrid(s), st);
         }
         if (p.form == 1) {
             const float2* G = reinterpret_cast<const float2*>(w + p.off_G);
@@ -743,32 +744,62 @@ extern "C" size_t sfa_pwd_work_bytes(const sfa_pwd_shape* s) {
     return p.total;
 }
 
-extern "C" int sfa_pwd_apply(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* Y_Q,
-                             const sfa_c128* d, const void* X, void* out, void* work, size_t work_bytes,
-                             void* stream) {
+// Operator preparation (everything that depends on Y_L / Y_Q only): group products or split operand planes,
+// written into `work`.  Valid until Y_L, Y_Q or the shape change; sfa_pwd_run reads it.
+extern "C" int sfa_pwd_prepare(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* Y_Q, void* work,
+                               size_t work_bytes, void* stream) {
+    Plan p;
+    int rc = make_plan(s, &p);
+    if (rc != SFA_OK) return rc;
+    if (!Y_L || !Y_Q || !work) return SFA_ERR_INVALID;
+    if (work_bytes < p.total) return SFA_ERR_WORKSPACE;
+    unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
+    return pwd_prepare(s, p, reinterpret_cast<const double2*>(Y_L), reinterpret_cast<const double2*>(Y_Q), w,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int sfa_pwd_run(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* d, const void* X, void* out,
+                           float* power, void* work, size_t work_bytes, void* stream) {
     Plan p;
     int rc = make_plan(s, &p);
     if (rc != SFA_OK) return rc;
     if (s->F == 0) return SFA_OK;
-    if (!Y_L || !Y_Q || !d || !X || !out || !work) return SFA_ERR_INVALID;
+    if (!Y_L || !d || !X || !out || !work) return SFA_ERR_INVALID;
+    if (power && !is_c64(s)) return SFA_ERR_UNSUPPORTED;
     if (work_bytes < p.total) return SFA_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
     const double2* yl = reinterpret_cast<const double2*>(Y_L);
     const double2* dd = reinterpret_cast<const double2*>(d);
-    rc = pwd_prepare(s, p, yl, reinterpret_cast<const double2*>(Y_Q), w, st);
-    if (rc != SFA_OK) return rc;
     const size_t eb = elem_bytes(s);
-    if (is_c64(s) && p.form == 1 && !p.fused && s->F > p.fc)
-        return pwd_steering_pipelined(s, p, dd, reinterpret_cast<const float2*>(X), reinterpret_cast<float2*>(out), w, st);
-    for (long long f0 = 0; f0 < s->F; f0 += p.fc) {
-        const long long nf = (s->F - f0 < p.fc) ? (s->F - f0) : p.fc;
-        rc = pwd_run_bins(s, p, nf, yl, dd + f0 * s->Cd,
-                          reinterpret_cast<const unsigned char*>(X) + (size_t)f0 * s->Q * s->T * eb,
-                          reinterpret_cast<unsigned char*>(out) + (size_t)f0 * s->L * p.Old * eb, w, st);
-        if (rc != SFA_OK) return rc;
+    if (is_c64(s) && p.form == 1 && !p.fused && s->F > p.fc) {
+        rc = pwd_steering_pipelined(s, p, dd, reinterpret_cast<const float2*>(X), reinterpret_cast<float2*>(out), w, st);
+    } else {
+        for (long long f0 = 0; f0 < s->F && rc == SFA_OK; f0 += p.fc) {
+            const long long nf = (s->F - f0 < p.fc) ? (s->F - f0) : p.fc;
+            rc = pwd_run_bins(s, p, nf, yl, dd + f0 * s->Cd,
+                              reinterpret_cast<const unsigned char*>(X) + (size_t)f0 * s->Q * s->T * eb,
+                              reinterpret_cast<unsigned char*>(out) + (size_t)f0 * s->L * p.Old * eb, w, st,
+                              (power && p.fused) ? power + f0 * s->L : nullptr);
+        }
     }
+    if (rc != SFA_OK) return rc;
+    // every path but the fused kernel (which accumulates the map in its epilogue) takes one more pass over the beams
+    if (power && !p.fused)
+        return sfa_power_map(s->F * s->L, s->T, p.Old, reinterpret_cast<const sfa_c64*>(out), power, stream);
     return SFA_OK;
+}
+
+extern "C" int sfa_pwd_apply(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* Y_Q,
+                             const sfa_c128* d, const void* X, void* out, void* work, size_t work_bytes,
+                             void* stream) {
+    if (s && s->F == 0) {
+        Plan p;
+        return make_plan(s, &p);
+    }
+    int rc = sfa_pwd_prepare(s, Y_L, Y_Q, work, work_bytes, stream);
+    if (rc != SFA_OK) return rc;
+    return sfa_pwd_run(s, Y_L, d, X, out, nullptr, work, work_bytes, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -42,7 +42,11 @@ namespace fused {
 constexpr int kTileL = 128;                         // look directions per task (TMEM lanes)
 constexpr int kTileT = 64;                          // frames per MMA step
 constexpr int kMaxK = 64;                           // microphones (complex k) resident in TMEM
-constexpr int kStages = 2;
+#ifndef SFA_FUSED_STAGES
+#define SFA_FUSED_STAGES 2
+#endif
+constexpr int kStages = SFA_FUSED_STAGES;
+constexpr int kTailMaxRows = 16;                    // L mod 128 up to this many rows goes to the CUDA-core tail kernel
 constexpr int kBoxK = 32;                           // fp32 per 128-byte swizzle row
 constexpr int kBoxBytes = kTileT * kBoxK * 4;       // 8 KB
 constexpr int kStageBytes = 4 * 2 * kBoxBytes;      // 4 planes x 2 k-boxes = 64 KB
@@ -66,7 +70,8 @@ constexpr int kStoreRing = SFA_FUSED_RING;          // staging slots (one pass =
 constexpr int kStoreWarpBytes = kStoreRing * 2 * kStoreBoxBytes;
 
 struct Params {
-    long long F, L, T;
+    long long F, L, T;           // bins, look directions handled by this kernel (a multiple of 128 when the tail kernel takes the rest), frames
+    long long Lrows;             // rows per bin of the beam tensor / power map (all look directions)
     int K;                       // microphones (<= 64)
     int ksteps, kboxes;          // ceil(K/8), ceil(K/32)
     int ngroups;                 // columns of d (<= NG)
@@ -75,6 +80,7 @@ struct Params {
     const float2* d;             // [F][ngroups] complex64
     int ltiles, lt_groups, csize, t_tiles;
     long long groups;            // F * lt_groups
+    float* power;                // nullable: [F][L] mean_t |q|^2, accumulated in the epilogue (a CTA owns whole rows)
     int debug;                   // timing attribution (SFA_DEBUG_HOOKS builds only): 1 no TMA stores, 2 no build FMAs,
                                  // 4 no staging writes, 8 no MMAs, 16 no operand loads
 };
@@ -364,6 +370,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             decode(grp, f, lt);
             if (lt >= prm.ltiles) continue;
             const int l0 = lt * kTileL + quarter * 32;
+            float psum = 0.f;                                    // sum_t |q[f, l0 + lane, t]|^2
             for (int tt = 0; tt < prm.t_tiles; ++tt) {
                 mbar_wait(&bars->acc_full[acc], acc_phase);
                 tcgen05_fence_after();
@@ -382,6 +389,16 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     }
                     const long long t0 = (long long)tt * kTileT + pass * 32;
                     if (t0 >= prm.T || l0 >= prm.L) continue;                   // warp-uniform
+                    if (prm.power) {
+                        const int nval = (prm.T - t0 >= 32) ? 32 : (int)(prm.T - t0);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < nval) {
+                                const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
+                                psum = fmaf(xr, xr, fmaf(xi, xi, psum));
+                            }
+                        }
+                    }
                     unsigned char* const sbuf = my_store + (size_t)buf * 2 * kStoreBoxBytes;
                     // the stores issued from this slot kStoreRing passes ago must have finished reading it
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStoreRing - 1) : "memory");
@@ -413,6 +430,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     acc_phase ^= 1;
                 }
             }
+            if (prm.power && l0 + lane < prm.L) prm.power[f * prm.Lrows + l0 + lane] = psum / (float)prm.T;
         }
     }
 
@@ -474,6 +492,87 @@ x_split_kernel(const float2* __restrict__ X, long long F, int Q, long long T, in
             }
         }
         __syncthreads();
+    }
+}
+
+// The last few look directions when L is not a multiple of 128 (icosahedral / Fibonacci grids: 42, 162, 642,
+// 2562 = 20 x 128 + 2): a whole 128-row tensor-core tile -- and a ghost tile for its cluster partner -- for two
+// rows costs 9 % of the fused kernel's time.  These rows are cheap on the CUDA cores instead:
+//   out[f, Lm + r, t] = sum_q A_f[r, q] X[f, q, t],   A_f[r, q] = sum_g d_f[g] G_g[Lm + r, q]     (FP32 FMA)
+// One CTA per bin; the steering rows are built in shared memory from the builders' table.
+template <int RMAX>
+__global__ void __launch_bounds__(256)
+pwd_tail_rows_kernel(const float4* __restrict__ G2_last, int ngroups, int Kh, const float2* __restrict__ d,
+                     const float2* __restrict__ X, int Q, long long T, float2* __restrict__ out, long long L,
+                     long long Lm, int rem, long long ldo, float* __restrict__ power) {
+    extern __shared__ float2 sA[];                                  // [rem][2 * Kh]
+    __shared__ float spow[8][RMAX];
+    const long long f = blockIdx.x;
+    const int Kc = 2 * Kh;
+    for (int i = threadIdx.x; i < rem * Kh; i += blockDim.x) {
+        const int r = i / Kh, j = i - r * Kh;
+        float ar0 = 0.f, ai0 = 0.f, ar1 = 0.f, ai1 = 0.f;
+        for (int g = 0; g < ngroups; ++g) {
+            const float2 dg = __ldg(d + f * ngroups + g);
+            const float4 v = __ldg(G2_last + ((size_t)g * Kh + j) * kTileL + r);
+            ar0 = fmaf(dg.x, v.x, ar0);
+            ar0 = fmaf(-dg.y, v.y, ar0);
+            ai0 = fmaf(dg.x, v.y, ai0);
+            ai0 = fmaf(dg.y, v.x, ai0);
+            ar1 = fmaf(dg.x, v.z, ar1);
+            ar1 = fmaf(-dg.y, v.w, ar1);
+            ai1 = fmaf(dg.x, v.w, ai1);
+            ai1 = fmaf(dg.y, v.z, ai1);
+        }
+        sA[r * Kc + 2 * j] = make_float2(ar0, ai0);
+        sA[r * Kc + 2 * j + 1] = make_float2(ar1, ai1);
+    }
+    __syncthreads();
+    for (int r0 = 0; r0 < rem; r0 += RMAX) {
+        float psum[RMAX];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) psum[r] = 0.f;
+        for (long long t = threadIdx.x; t < T; t += blockDim.x) {
+            float accr[RMAX], acci[RMAX];
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) accr[r] = acci[r] = 0.f;
+            const float2* xp = X + f * Q * T + t;
+            for (int q = 0; q < Q; ++q) {
+                const float2 x = __ldg(xp + (long long)q * T);
+#pragma unroll
+                for (int r = 0; r < RMAX; ++r) {
+                    if (r0 + r < rem) {
+                        const float2 a = sA[(r0 + r) * Kc + q];
+                        accr[r] = fmaf(a.x, x.x, accr[r]);
+                        accr[r] = fmaf(-a.y, x.y, accr[r]);
+                        acci[r] = fmaf(a.x, x.y, acci[r]);
+                        acci[r] = fmaf(a.y, x.x, acci[r]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                if (r0 + r < rem) {
+                    out[(f * L + Lm + r0 + r) * ldo + t] = make_float2(accr[r], acci[r]);
+                    psum[r] = fmaf(accr[r], accr[r], fmaf(acci[r], acci[r], psum[r]));
+                }
+            }
+        }
+        if (power) {                                                 // block reduction of sum_t |q|^2 per row
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                float p = psum[r];
+                for (int off = 16; off; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
+                if ((threadIdx.x & 31) == 0) spow[threadIdx.x >> 5][r] = p;
+            }
+            __syncthreads();
+            if (threadIdx.x < RMAX && r0 + threadIdx.x < rem) {
+                float p = 0.f;
+                for (int w = 0; w < 8; ++w) p += spow[w][threadIdx.x];
+                power[f * L + Lm + r0 + threadIdx.x] = p / (float)T;
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -556,7 +655,8 @@ int launch_group_products_g2(const double2* YL, const double2* YQt, long long L,
 
 // q[f] = (sum_g d[f][g] G_g) X[f] for nf bins.  d: complex64 [nf][Cd]; X: [nf][Q][T]; out: [nf][L][ldo].
 int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd, const float* G2, const float2* d,
-                     const float2* X, float* Xs, float2* out, long long ldo, int hybrid, cudaStream_t st) {
+                     const float2* X, float* Xs, float2* out, long long ldo, float* power, int hybrid,
+                     cudaStream_t st) {
     using namespace fused;
     if (nf <= 0) return SFA_OK;
     EncodeTiledFn encode = get_encode_fn();
@@ -572,6 +672,10 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
         prof_aux_end(st);
         SFA_LAUNCH_CHECK();
     }
+    // look directions beyond the last full 128-row tile: few of them -> CUDA-core tail kernel (no ragged tile, no ghost CTA)
+    const long long rem = L % kTileL;
+    const bool tail = rem > 0 && rem <= kTailMaxRows && L > kTileL;
+    const long long Lmain = tail ? L - rem : L;
     CUtensorMap xmap, omap;
     {
         cuuint64_t gdim[3] = {(cuuint64_t)Q, (cuuint64_t)T, (cuuint64_t)(4 * nf)};
@@ -586,7 +690,7 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
             return SFA_ERR_CUDA;
         }
         // beams as fp32 [nf][L][2*ldo]; store box = 32 rows x 32 fp32 (16 frames), SWIZZLE_128B staging
-        cuuint64_t odim[3] = {(cuuint64_t)(2 * T), (cuuint64_t)L, (cuuint64_t)nf};
+        cuuint64_t odim[3] = {(cuuint64_t)(2 * T), (cuuint64_t)Lmain, (cuuint64_t)nf};
         cuuint64_t ostr[2] = {(cuuint64_t)ldo * 8, (cuuint64_t)L * ldo * 8};
         cuuint32_t obox[3] = {32, 32, 1};
         r = encode(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)out, odim, ostr, obox, estr,
@@ -599,7 +703,8 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     }
     Params prm;
     prm.F = nf;
-    prm.L = L;
+    prm.L = Lmain;
+    prm.Lrows = L;
     prm.T = T;
     prm.K = (int)Q;
     prm.ksteps = (int)ceil_div(Q, 8);
@@ -608,11 +713,12 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     prm.G2 = reinterpret_cast<const float4*>(G2);
     prm.Kh = prm.ksteps * 4;
     prm.d = d;
-    prm.ltiles = (int)ceil_div(L, kTileL);
+    prm.ltiles = (int)ceil_div(Lmain, kTileL);
     prm.csize = (prm.ltiles >= 2 && !options().no_cluster) ? 2 : 1;
     prm.lt_groups = (prm.ltiles + prm.csize - 1) / prm.csize;
     prm.t_tiles = (int)ceil_div(T, kTileT);
     prm.groups = nf * prm.lt_groups;
+    prm.power = power;
 #ifdef SFA_DEBUG_HOOKS
     prm.debug = options().fused_debug;
 #else
@@ -654,6 +760,13 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
         return SFA_ERR_CUDA;
     }
     SFA_LAUNCH_CHECK();
+    if (tail) {
+        const float4* g2_last = prm.G2 + (size_t)(Lmain / kTileL) * Cd * prm.Kh * kTileL;
+        const size_t tsmem = (size_t)rem * 2 * prm.Kh * sizeof(float2);
+        pwd_tail_rows_kernel<8><<<(unsigned)nf, 256, tsmem, st>>>(g2_last, Cd, prm.Kh, d, X, (int)Q, T, out, L, Lmain,
+                                                                   (int)rem, ldo, power);
+        SFA_LAUNCH_CHECK();
+    }
     return SFA_OK;
 }
 

@@ -175,36 +175,95 @@ def synthesize(Y_mic, bn, Y_src, precision="c128"):
 
 
 class PwdPlan:
-    """Reusable device-side plan: workspace allocated once, operators kept resident."""
+    """Reusable device-side plan: workspace allocated once, operators kept resident.
+
+    The operator preparation (group products of Y_look / Y_mic, `sfa_pwd_prepare`) runs when the plan is
+    created and again only after `Y_look` / `Y_mic` have been re-assigned; `dn` may be re-assigned freely
+    (it is read by every call).  ``plan(X, out=..., power=...)``: `power` is an optional float32 [F, L]
+    tensor (or True to allocate one, then available as ``plan.power``) that receives the beam power map
+    mean_t |q|^2 -- accumulated inside the fused steering kernel, i.e. without another pass over q."""
 
     def __init__(self, Y_look, dn, Y_mic, T, precision="c64", form="auto", device=None):
         self.lib = _lib.require_cuda()
         dev = device if device is not None else _device_of(Y_look, dn, Y_mic)
         self.dev = dev
+        self.precision = precision
         self.cdtype = torch.complex128 if precision == "c128" else torch.complex64
-        self.Y_look = as_complex_tensor(Y_look, dev)
-        self.Y_mic = as_complex_tensor(Y_mic, dev)
+        self._Y_look = as_complex_tensor(Y_look, dev)
+        self._Y_mic = as_complex_tensor(Y_mic, dev)
         dn = as_complex_tensor(dn, dev)
         self.dn = dn[None, :] if dn.ndim == 1 else dn
-        F, Q = self.dn.shape[0], self.Y_mic.shape[0]
-        self.shape = _shape_of(self.Y_look, self.dn, self.Y_mic, F, Q, int(T), precision, form)
+        F, Q = self.dn.shape[0], self._Y_mic.shape[0]
+        self.shape = _shape_of(self._Y_look, self.dn, self._Y_mic, F, Q, int(T), precision, form)
         _check_c64_range(self.dn, precision)      # checked once per plan; re-assigned `dn` is the caller's business
         self.nbytes = self.lib.sfa_pwd_work_bytes(ctypes.byref(self.shape))
         if self.nbytes == 0:
             raise ValueError("unsupported plane-wave-decomposition shape")
         self.work = torch.empty(self.nbytes, dtype=torch.uint8, device=dev)
-        self.out_shape = (F, self.Y_look.shape[0], int(T))
+        self.out_shape = (F, self._Y_look.shape[0], int(T))
+        self.power = None
+        self._prepared_ld = None
 
-    def __call__(self, X, out=None):
+    # re-assigning an operator invalidates the prepared group products
+    @property
+    def Y_look(self):
+        return self._Y_look
+
+    @Y_look.setter
+    def Y_look(self, v):
+        self._Y_look = as_complex_tensor(v, self.dev)
+        self._prepared_ld = None
+
+    @property
+    def Y_mic(self):
+        return self._Y_mic
+
+    @Y_mic.setter
+    def Y_mic(self, v):
+        self._Y_mic = as_complex_tensor(v, self.dev)
+        self._prepared_ld = None
+
+    def prepare(self):
+        """(Re)compute everything that depends on Y_look / Y_mic only."""
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.sfa_pwd_prepare(ctypes.byref(self.shape), _lib.ptr(self._Y_look), _lib.ptr(self._Y_mic),
+                                                _lib.ptr(self.work), self.nbytes, _lib.stream_ptr(self.dev)))
+        self._prepared_ld = self.shape.out_ld
+
+    def __call__(self, X, out=None, power=None):
         if X.dtype != self.cdtype or not X.is_contiguous() or X.device != self.dev:
             raise ValueError("X must be a contiguous {} tensor on {}".format(self.cdtype, self.dev))
+        if tuple(X.shape) != (self.out_shape[0], self._Y_mic.shape[0], self.out_shape[2]):
+            raise ValueError("X must have shape (F, Q, T) = {}".format((self.out_shape[0], self._Y_mic.shape[0],
+                                                                         self.out_shape[2])))
         if out is None:
             out = _alloc_out(*self.out_shape, self.cdtype, self.dev)
-        self.shape.out_ld = _check_out(out, *self.out_shape, self.cdtype, self.dev)
+        ld = _check_out(out, *self.out_shape, self.cdtype, self.dev)
+        # the plan (kernel choice, workspace layout) depends on the row pitch of `out`: prepare again if it changed
+        if self._prepared_ld is None or ld != self.shape.out_ld:
+            self.shape.out_ld = ld
+            if self.lib.sfa_pwd_work_bytes(ctypes.byref(self.shape)) > self.nbytes:
+                self.nbytes = self.lib.sfa_pwd_work_bytes(ctypes.byref(self.shape))
+                self.work = torch.empty(self.nbytes, dtype=torch.uint8, device=self.dev)
+            self.prepare()
+        pm = None
+        if power is not None and power is not False:
+            if self.precision == "c128":
+                raise ValueError("the fused power map is available for the complex64 precisions")
+            F, L = self.out_shape[0], self.out_shape[1]
+            if power is True:
+                if self.power is None:
+                    self.power = torch.empty((F, L), dtype=torch.float32, device=self.dev)
+                pm = self.power
+            else:
+                pm = power
+                if tuple(pm.shape) != (F, L) or pm.dtype != torch.float32 or not pm.is_contiguous() or pm.device != self.dev:
+                    raise ValueError("power must be a contiguous float32 tensor of shape (F, L)")
+                self.power = pm
         with torch.cuda.device(self.dev):
-            _lib.check(self.lib.sfa_pwd_apply(ctypes.byref(self.shape), _lib.ptr(self.Y_look), _lib.ptr(self.Y_mic),
-                                              _lib.ptr(self.dn), _lib.ptr(X), _lib.ptr(out), _lib.ptr(self.work),
-                                              self.nbytes, _lib.stream_ptr(self.dev)))
+            _lib.check(self.lib.sfa_pwd_run(ctypes.byref(self.shape), _lib.ptr(self._Y_look), _lib.ptr(self.dn),
+                                            _lib.ptr(X), _lib.ptr(out), _lib.ptr(pm), _lib.ptr(self.work),
+                                            self.nbytes, _lib.stream_ptr(self.dev)))
         return out
 
 

@@ -38,18 +38,25 @@ def test_examples_time_domain(golden, name):
 
 @pytest.mark.parametrize("F,C,n", [(1025, 37, None), (1024, 10, 2048), (33, 1, None), (9, 5, 15), (9, 5, 16), (9, 4, 7),
                                    (100, 3, 198), (100, 6, 256), (300, 2, 100), (2, 3, None), (513, 64, 1024),
-                                   (4097, 3, None), (70, 9, 139)])
+                                   (4097, 3, None), (70, 9, 139), (1024, 5, None), (2049, 4, None)])
 def test_irfft_random(F, C, n):
     import sfa_numpy_b200 as micarray
+    from sfa_numpy_b200 import _lib
     rng = np.random.default_rng(F * 131 + C)
     q = rng.standard_normal((F, C)) + 1j * rng.standard_normal((F, C))
+    n_eff = 2 * (F - 1) if n is None else n
     for shift in (False, True):
         ref = np.fft.irfft(q, n=n, axis=0)
         if shift:
             ref = np.fft.fftshift(ref, axes=0)
-        out = micarray.fft.irfft(q, n=n, shift=shift)
-        assert tuple(out.shape) == ref.shape
-        assert relmax(cpu(out), ref) < 1e-10, (F, C, n, shift)
+        if n_eff > 4096:
+            # documented limit of the FP64 kernel (shared-memory FFT): power-of-two length <= 4096
+            with pytest.raises(_lib.SfaError):
+                micarray.fft.irfft(q, n=n, shift=shift)
+        else:
+            out = micarray.fft.irfft(q, n=n, shift=shift)
+            assert tuple(out.shape) == ref.shape
+            assert relmax(cpu(out), ref) < 1e-10, (F, C, n, shift)
         out32 = micarray.fft.irfft(q.astype(np.complex64), n=n, shift=shift)
         assert relmax(cpu(out32), ref) < 1e-5, (F, C, n, shift)
 

@@ -324,7 +324,9 @@ def test_pwd_fused_kernel_shapes(mic, precision):
     rng = np.random.default_rng(11)
     #        N  Q   L    F   T
     cases = [(2, 9, 5, 3, 2), (3, 16, 128, 2, 64), (3, 20, 129, 5, 70), (4, 36, 300, 7, 130), (2, 12, 700, 4, 18),
-             (5, 64, 385, 3, 200), (7, 64, 2562, 2, 90), (1, 5, 257, 9, 34), (8, 64, 130, 3, 938)]
+             (5, 64, 385, 3, 200), (7, 64, 2562, 2, 90), (1, 5, 257, 9, 34), (8, 64, 130, 3, 938),
+             # L mod 128 = 16 (CUDA-core tail kernel, two row groups) and 17 (ragged tensor-core tile + ghost CTA)
+             (3, 20, 144, 2, 40), (3, 20, 145, 2, 40), (3, 17, 266, 3, 333)]
     for (N, Q, L, F, T) in cases:
         az, co, w = O.fibonacci_grid(Q)
         azl, col, _ = O.fibonacci_grid(L)
@@ -343,6 +345,21 @@ def test_pwd_fused_kernel_shapes(mic, precision):
             lib.sfa_set_option(b"no_fused", 0.0)
         assert bin_err(cpu(q_s), ref) < TOL64
         assert bin_err(cpu(q_f), cpu(q_s).astype(np.complex128)) < TOL64
+        # plan API: prepared operators reused over calls, power map out of the kernel's epilogue (fused) or from
+        # the extra pass (slab pipeline), both against NumPy
+        pm_ref = np.mean(np.abs(ref) ** 2, axis=2)
+        for nofused in (0.0, 1.0):
+            try:
+                _lib.check(lib.sfa_set_option(b"no_fused", nofused))
+                plan = S.PwdPlan(Yq_ref, dn_ref, Yp_ref, T, precision=precision, form="steering")
+                q1 = plan(Xd, power=True)
+                q2 = plan(Xd, power=True)                    # second call: no re-preparation
+            finally:
+                lib.sfa_set_option(b"no_fused", 0.0)
+            assert torch.equal(q1, q2) and bin_err(cpu(q1), ref) < TOL64
+            pm = cpu(plan.power)
+            assert pm.shape == pm_ref.shape
+            assert np.max(np.abs(pm - pm_ref) / np.max(pm_ref, axis=1, keepdims=True)) < 1e-5, (N, Q, L, F, T, nofused)
     # per-column filters (circular array: d has M = 2N+1 columns, every column its own group)
     N, Q, L, F, T = 6, 13, 200, 6, 96
     pol = np.linspace(0, 2 * np.pi, Q, endpoint=False)
