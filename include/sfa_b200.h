@@ -208,6 +208,14 @@ int sfa_pwd_host_create(sfa_pwd_host_ctx** ctx, const sfa_pwd_shape* s, int devi
 int sfa_pwd_host_set_operators(sfa_pwd_host_ctx* ctx, const sfa_c128* Y_L_host,
                                const sfa_c128* Y_Q_host, const sfa_c128* d_host);
 int sfa_pwd_host_run(sfa_pwd_host_ctx* ctx, const void* X_host, void* out_host);
+/* Operators that already live on the device (the outputs of sfa_sht_matrix / sfa_radial_filter on `stream`):
+ * device-to-device copies, no round trip through the host. */
+int sfa_pwd_host_set_operators_dev(sfa_pwd_host_ctx* ctx, const sfa_c128* Y_L_dev, const sfa_c128* Y_Q_dev,
+                                   const sfa_c128* d_dev, void* stream);
+/* As sfa_pwd_host_run, with the beam power map mean_t |q|^2 ([F, L] float32, host) as a second -- or, when
+ * out_host is NULL, the only -- result: the "beam map" reading of the metric moves 4 F L bytes back over PCIe
+ * instead of 8 F L T. */
+int sfa_pwd_host_run_power(sfa_pwd_host_ctx* ctx, const void* X_host, void* out_host, float* power_host);
 int sfa_pwd_host_destroy(sfa_pwd_host_ctx* ctx);
 /* pinned host memory helpers for the host path */
 int sfa_host_alloc(void** p, size_t bytes);

@@ -12,3 +12,4 @@ __version__ = "0.1.0"
 from . import modal
 from . import util
 from . import fft
+from . import pipeline

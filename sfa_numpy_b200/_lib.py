@@ -61,6 +61,8 @@ SIGNATURES = {
     "sfa_pwd_host_create": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(PwdShape), c_int, c_int64]),
     "sfa_pwd_host_set_operators": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfa_pwd_host_run": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "sfa_pwd_host_set_operators_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sfa_pwd_host_run_power": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfa_pwd_host_destroy": (c_int, [c_void_p]),
     "sfa_power_map": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "sfa_irfft_work_bytes": (c_size_t, [c_int64, c_int]),

@@ -813,6 +813,7 @@ struct sfa_pwd_host_ctx {
     cudaStream_t s_in, s_cmp, s_out;
     cudaEvent_t in_done[2], cmp_done[2], out_done[2];
     unsigned char *d_YL, *d_YQ, *d_d, *d_work, *d_X[2], *d_O[2];
+    float* d_P;                      // power map [F][L], allocated on first use
     bool operators_set;
 };
 
@@ -883,9 +884,39 @@ extern "C" int sfa_pwd_host_set_operators(sfa_pwd_host_ctx* c, const sfa_c128* Y
 }
 
 extern "C" int sfa_pwd_host_run(sfa_pwd_host_ctx* c, const void* X_host, void* out_host) {
-    if (!c || !X_host || !out_host || !c->operators_set) return SFA_ERR_INVALID;
+    return sfa_pwd_host_run_power(c, X_host, out_host, nullptr);
+}
+
+extern "C" int sfa_pwd_host_set_operators_dev(sfa_pwd_host_ctx* c, const sfa_c128* Y_L, const sfa_c128* Y_Q,
+                                              const sfa_c128* d, void* stream) {
+    if (!c || !Y_L || !Y_Q || !d) return SFA_ERR_INVALID;
     const sfa_pwd_shape* s = &c->shape;
     SFA_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t src = (cudaStream_t)stream;
+    // order after the producer of the operators (stages 1-2 on the caller's stream), then copy device to device
+    cudaEvent_t ev;
+    SFA_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    SFA_CUDA_CHECK(cudaEventRecord(ev, src));
+    SFA_CUDA_CHECK(cudaStreamWaitEvent(c->s_cmp, ev, 0));
+    SFA_CUDA_CHECK(cudaEventDestroy(ev));
+    SFA_CUDA_CHECK(cudaMemcpyAsync(c->d_YL, Y_L, (size_t)s->L * s->M * 16, cudaMemcpyDeviceToDevice, c->s_cmp));
+    SFA_CUDA_CHECK(cudaMemcpyAsync(c->d_YQ, Y_Q, (size_t)s->Q * s->M * 16, cudaMemcpyDeviceToDevice, c->s_cmp));
+    SFA_CUDA_CHECK(cudaMemcpyAsync(c->d_d, d, (size_t)s->F * s->Cd * 16, cudaMemcpyDeviceToDevice, c->s_cmp));
+    unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)c->d_work + 255) & ~(uintptr_t)255);
+    int rc = pwd_prepare(s, c->plan, reinterpret_cast<const double2*>(c->d_YL),
+                         reinterpret_cast<const double2*>(c->d_YQ), w, c->s_cmp);
+    if (rc != SFA_OK) return rc;
+    SFA_CUDA_CHECK(cudaStreamSynchronize(c->s_cmp));      // the caller may overwrite its operator buffers now
+    c->operators_set = true;
+    return SFA_OK;
+}
+
+extern "C" int sfa_pwd_host_run_power(sfa_pwd_host_ctx* c, const void* X_host, void* out_host, float* power_host) {
+    if (!c || !X_host || (!out_host && !power_host) || !c->operators_set) return SFA_ERR_INVALID;
+    const sfa_pwd_shape* s = &c->shape;
+    if (power_host && !is_c64(s)) return SFA_ERR_UNSUPPORTED;
+    SFA_CUDA_CHECK(cudaSetDevice(c->device));
+    if (power_host && !c->d_P) SFA_CUDA_CHECK(cudaMalloc(&c->d_P, (size_t)(s->F > 0 ? s->F : 1) * s->L * sizeof(float)));
     const size_t eb = elem_bytes(s);
     unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)c->d_work + 255) & ~(uintptr_t)255);
     const size_t x_bin = (size_t)s->Q * s->T * eb, o_bin = (size_t)s->L * s->T * eb;
@@ -904,19 +935,30 @@ extern "C" int sfa_pwd_host_run(sfa_pwd_host_ctx* c, const void* X_host, void* o
         if (it >= 2) SFA_CUDA_CHECK(cudaStreamWaitEvent(c->s_cmp, c->out_done[slot], 0));
         for (long long g0 = 0; g0 < nf; g0 += c->plan.fc) {
             const long long ng = (nf - g0 < c->plan.fc) ? (nf - g0) : c->plan.fc;
+            float* pw = power_host ? c->d_P + (f0 + g0) * s->L : nullptr;
             int rc = pwd_run_bins(s, c->plan, ng, reinterpret_cast<const double2*>(c->d_YL),
                                   reinterpret_cast<const double2*>(c->d_d) + (f0 + g0) * s->Cd,
-                                  c->d_X[slot] + g0 * x_bin, c->d_O[slot] + g0 * o_bin_dev, w, c->s_cmp);
+                                  c->d_X[slot] + g0 * x_bin, c->d_O[slot] + g0 * o_bin_dev, w, c->s_cmp,
+                                  c->plan.fused ? pw : nullptr);
             if (rc != SFA_OK) return rc;
+            if (pw && !c->plan.fused) {
+                rc = sfa_power_map(ng * s->L, s->T, s->out_ld, reinterpret_cast<const sfa_c64*>(c->d_O[slot] + g0 * o_bin_dev),
+                                   pw, c->s_cmp);
+                if (rc != SFA_OK) return rc;
+            }
         }
         SFA_CUDA_CHECK(cudaEventRecord(c->cmp_done[slot], c->s_cmp));
         SFA_CUDA_CHECK(cudaStreamWaitEvent(c->s_out, c->cmp_done[slot], 0));
         // rows are compacted by the copy engine (device pitch out_ld -> host pitch T)
-        SFA_CUDA_CHECK(cudaMemcpy2DAsync(reinterpret_cast<unsigned char*>(out_host) + f0 * o_bin, (size_t)s->T * eb,
-                                         c->d_O[slot], (size_t)s->out_ld * eb, (size_t)s->T * eb,
-                                         (size_t)nf * s->L, cudaMemcpyDeviceToHost, c->s_out));
+        if (out_host)
+            SFA_CUDA_CHECK(cudaMemcpy2DAsync(reinterpret_cast<unsigned char*>(out_host) + f0 * o_bin, (size_t)s->T * eb,
+                                             c->d_O[slot], (size_t)s->out_ld * eb, (size_t)s->T * eb,
+                                             (size_t)nf * s->L, cudaMemcpyDeviceToHost, c->s_out));
         SFA_CUDA_CHECK(cudaEventRecord(c->out_done[slot], c->s_out));
     }
+    if (power_host)
+        SFA_CUDA_CHECK(cudaMemcpyAsync(power_host, c->d_P, (size_t)s->F * s->L * sizeof(float), cudaMemcpyDeviceToHost,
+                                       c->s_cmp));
     SFA_CUDA_CHECK(cudaStreamSynchronize(c->s_out));
     SFA_CUDA_CHECK(cudaStreamSynchronize(c->s_cmp));
     return SFA_OK;
@@ -937,6 +979,7 @@ extern "C" int sfa_pwd_host_destroy(sfa_pwd_host_ctx* c) {
     if (c->d_YQ) cudaFree(c->d_YQ);
     if (c->d_d) cudaFree(c->d_d);
     if (c->d_work) cudaFree(c->d_work);
+    if (c->d_P) cudaFree(c->d_P);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
     if (c->s_out) cudaStreamDestroy(c->s_out);

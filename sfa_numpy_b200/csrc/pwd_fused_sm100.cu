@@ -46,6 +46,10 @@ constexpr int kMaxK = 64;                           // microphones (complex k) r
 #define SFA_FUSED_STAGES 2
 #endif
 constexpr int kStages = SFA_FUSED_STAGES;
+#ifndef SFA_FUSED_PREFETCH
+#define SFA_FUSED_PREFETCH 2
+#endif
+constexpr int kPrefetch = SFA_FUSED_PREFETCH;       // L2 prefetch distance of the spectra stream, in frame tiles
 constexpr int kTailMaxRows = 16;                    // L mod 128 up to this many rows goes to the CUDA-core tail kernel
 constexpr int kBoxK = 32;                           // fp32 per 128-byte swizzle row
 constexpr int kBoxBytes = kTileT * kBoxK * 4;       // 8 KB
@@ -184,6 +188,28 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
+                    }
+                    // L2 prefetch of the tile kPrefetch steps ahead (the ten clusters working on a bin reach a new
+                    // frame tile together, so without it every one of them waits out a DRAM miss)
+                    if (kPrefetch > 0) {
+                        int ptt = tt + kPrefetch;
+                        long long pgrp = grp;
+                        while (ptt >= prm.t_tiles) {
+                            ptt -= prm.t_tiles;
+                            pgrp += n_clusters;
+                        }
+                        if (pgrp < prm.groups) {
+                            const int pf = (int)(pgrp / prm.lt_groups);
+#pragma unroll
+                            for (int pl = 0; pl < 4; ++pl) {
+#pragma unroll
+                                for (int kb = 0; kb < 2; ++kb) {
+                                    if (kb >= prm.kboxes) continue;
+                                    if (csize == 1 || ((prm.kboxes > 1 ? pl * 2 + kb : pl) & 1) == (int)crank)
+                                        tma_prefetch_3d(&x_map, kb * kBoxK, ptt * kTileT, pf * 4 + pl);
+                                }
+                            }
+                        }
                     }
                 }
             }
@@ -445,134 +471,114 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     }
 }
 
-// X[f][q][t] complex64 -> Xs[f][4 planes][t][Kp] fp32, K-major (mic index contiguous), split for the B side of
-// the MMA: planes (re_hi, im_hi, re_x, im_x), x = lo (3xTF32) or packed bf16 (lo, hi) (hybrid).  32 x 32 tile
-// transpose through shared memory: reads coalesced along t, writes coalesced along q.
+// Pre-pass over the spectra, one CTA per bin:
+//  (1) X[f][q][t] complex64 -> Xs[f][4 planes][t][Kp] fp32, K-major (mic index contiguous), split for the B side
+//      of the MMA: planes (re_hi, im_hi, re_x, im_x), x = lo (3xTF32) or packed bf16 (lo, hi) (hybrid); a
+//      [64 q x 32 t] tile is transposed through shared memory (reads coalesced along t, writes along q);
+//  (2) the last few look directions when L is not a multiple of 128 (icosahedral / Fibonacci grids: 42, 162,
+//      642, 2562 = 20 x 128 + 2).  A whole 128-row tensor-core tile -- and a ghost tile for its cluster partner --
+//      for two rows costs 9 % of the fused kernel's time; on the CUDA cores, from the tile that is in shared
+//      memory anyway, they are almost free:
+//        out[f, Lm + r, t] = sum_q A_f[r, q] X[f, q, t],   A_f[r, q] = sum_g d_f[g] G_g[Lm + r, q]   (FP32 FMA)
+//      (+ their power-map entries: the CTA sees every frame of its bin, so no atomics).
+constexpr int kSplitT = 32;                          // frames per tile of the pre-pass
 __global__ void __launch_bounds__(256)
-x_split_kernel(const float2* __restrict__ X, long long F, int Q, long long T, int Kp, int hybrid,
-               float* __restrict__ Xs) {
-    __shared__ float2 tile[32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
-    const long long t_tiles = (T + 31) / 32;
-    const int q_tiles = (Kp + 31) / 32;
-    const long long tiles = F * t_tiles * q_tiles;
-    for (long long tile_id = blockIdx.x; tile_id < tiles; tile_id += gridDim.x) {
-        const long long f = tile_id / (t_tiles * q_tiles);
-        const long long r = tile_id - f * t_tiles * q_tiles;
-        const int qt = (int)(r / t_tiles);
-        const long long tt = r - (long long)qt * t_tiles;
-        const long long t0 = tt * 32;
-        const int q0 = qt * 32;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int q = q0 + ty + 8 * i;
-            const long long t = t0 + tx;
-            tile[ty + 8 * i][tx] = (q < Q && t < T) ? __ldg(X + (f * Q + q) * T + t) : make_float2(0.f, 0.f);
-        }
-        __syncthreads();
-        const long long plane = T * Kp;
-        float* base = Xs + f * 4 * plane;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long long t = t0 + ty + 8 * i;
-            const int q = q0 + tx;
-            if (t < T && q < Kp) {
-                const float2 v = tile[tx][ty + 8 * i];
-                const float hr = __uint_as_float(to_tf32(v.x)), hi = __uint_as_float(to_tf32(v.y));
-                float xr = v.x - hr, xi = v.y - hi;
-                if (hybrid) {                                          // B side: (lo, hi) = (even, odd) bf16 k
-                    xr = __uint_as_float(pack_bf16(xr, hr));
-                    xi = __uint_as_float(pack_bf16(xi, hi));
-                }
-                float* o = base + t * Kp + q;
-                o[0] = hr;
-                o[plane] = hi;
-                o[2 * plane] = xr;
-                o[3 * plane] = xi;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// The last few look directions when L is not a multiple of 128 (icosahedral / Fibonacci grids: 42, 162, 642,
-// 2562 = 20 x 128 + 2): a whole 128-row tensor-core tile -- and a ghost tile for its cluster partner -- for two
-// rows costs 9 % of the fused kernel's time.  These rows are cheap on the CUDA cores instead:
-//   out[f, Lm + r, t] = sum_q A_f[r, q] X[f, q, t],   A_f[r, q] = sum_g d_f[g] G_g[Lm + r, q]     (FP32 FMA)
-// One CTA per bin; the steering rows are built in shared memory from the builders' table.
-template <int RMAX>
-__global__ void __launch_bounds__(256)
-pwd_tail_rows_kernel(const float4* __restrict__ G2_last, int ngroups, int Kh, const float2* __restrict__ d,
-                     const float2* __restrict__ X, int Q, long long T, float2* __restrict__ out, long long L,
-                     long long Lm, int rem, long long ldo, float* __restrict__ power) {
-    extern __shared__ float2 sA[];                                  // [rem][2 * Kh]
-    __shared__ float spow[8][RMAX];
+x_split_tail_kernel(const float2* __restrict__ X, int Q, long long T, int Kp, int hybrid, float* __restrict__ Xs,
+                    const float4* __restrict__ G2_last, int ngroups, int Kh, const float2* __restrict__ d,
+                    float2* __restrict__ out, long long L, long long Lm, int rem, long long ldo,
+                    float* __restrict__ power) {
+    __shared__ float2 tile[kMaxK][kSplitT + 1];
+    __shared__ float2 sA[kTailMaxRows][kMaxK];                      // steering rows of the tail look directions
+    __shared__ float spow[kTailMaxRows];
     const long long f = blockIdx.x;
-    const int Kc = 2 * Kh;
-    for (int i = threadIdx.x; i < rem * Kh; i += blockDim.x) {
-        const int r = i / Kh, j = i - r * Kh;
-        float ar0 = 0.f, ai0 = 0.f, ar1 = 0.f, ai1 = 0.f;
-        for (int g = 0; g < ngroups; ++g) {
-            const float2 dg = __ldg(d + f * ngroups + g);
-            const float4 v = __ldg(G2_last + ((size_t)g * Kh + j) * kTileL + r);
-            ar0 = fmaf(dg.x, v.x, ar0);
-            ar0 = fmaf(-dg.y, v.y, ar0);
-            ai0 = fmaf(dg.x, v.y, ai0);
-            ai0 = fmaf(dg.y, v.x, ai0);
-            ar1 = fmaf(dg.x, v.z, ar1);
-            ar1 = fmaf(-dg.y, v.w, ar1);
-            ai1 = fmaf(dg.x, v.w, ai1);
-            ai1 = fmaf(dg.y, v.z, ai1);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    if (rem > 0) {
+        for (int i = threadIdx.x; i < rem * Kh; i += blockDim.x) {
+            const int r = i / Kh, j = i - r * Kh;
+            float ar0 = 0.f, ai0 = 0.f, ar1 = 0.f, ai1 = 0.f;
+            for (int g = 0; g < ngroups; ++g) {
+                const float2 dg = __ldg(d + f * ngroups + g);
+                const float4 v = __ldg(G2_last + ((size_t)g * Kh + j) * kTileL + r);
+                ar0 = fmaf(dg.x, v.x, ar0);
+                ar0 = fmaf(-dg.y, v.y, ar0);
+                ai0 = fmaf(dg.x, v.y, ai0);
+                ai0 = fmaf(dg.y, v.x, ai0);
+                ar1 = fmaf(dg.x, v.z, ar1);
+                ar1 = fmaf(-dg.y, v.w, ar1);
+                ai1 = fmaf(dg.x, v.w, ai1);
+                ai1 = fmaf(dg.y, v.z, ai1);
+            }
+            sA[r][2 * j] = make_float2(ar0, ai0);
+            sA[r][2 * j + 1] = make_float2(ar1, ai1);
         }
-        sA[r * Kc + 2 * j] = make_float2(ar0, ai0);
-        sA[r * Kc + 2 * j + 1] = make_float2(ar1, ai1);
+        if (threadIdx.x < kTailMaxRows) spow[threadIdx.x] = 0.f;
     }
-    __syncthreads();
-    for (int r0 = 0; r0 < rem; r0 += RMAX) {
-        float psum[RMAX];
+    const long long plane = T * Kp;
+    float* const base = Xs + f * 4 * plane;
+    const float2* const xf = X + f * Q * T;
+    float psum = 0.f;                                                // thread (r = tid / 32, t = tid % 32) of the tail
+    for (long long t0 = 0; t0 < T; t0 += kSplitT) {
+        __syncthreads();                                             // previous tile consumed (and sA complete)
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r) psum[r] = 0.f;
-        for (long long t = threadIdx.x; t < T; t += blockDim.x) {
-            float accr[RMAX], acci[RMAX];
+        for (int i = 0; i < kMaxK / 8; ++i) {
+            const int q = ty + 8 * i;
+            const long long t = t0 + tx;
+            tile[q][tx] = (q < Q && t < T) ? __ldg(xf + (long long)q * T + t) : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
 #pragma unroll
-            for (int r = 0; r < RMAX; ++r) accr[r] = acci[r] = 0.f;
-            const float2* xp = X + f * Q * T + t;
-            for (int q = 0; q < Q; ++q) {
-                const float2 x = __ldg(xp + (long long)q * T);
+        for (int i = 0; i < kSplitT / 8; ++i) {
+            const long long t = t0 + ty + 8 * i;
+            if (t < T) {
 #pragma unroll
-                for (int r = 0; r < RMAX; ++r) {
-                    if (r0 + r < rem) {
-                        const float2 a = sA[(r0 + r) * Kc + q];
-                        accr[r] = fmaf(a.x, x.x, accr[r]);
-                        accr[r] = fmaf(-a.y, x.y, accr[r]);
-                        acci[r] = fmaf(a.x, x.y, acci[r]);
-                        acci[r] = fmaf(a.y, x.x, acci[r]);
+                for (int h = 0; h < 2; ++h) {
+                    const int q = tx + 32 * h;
+                    if (q < Kp) {
+                        const float2 v = tile[q][ty + 8 * i];
+                        const float hr = __uint_as_float(to_tf32(v.x)), hi = __uint_as_float(to_tf32(v.y));
+                        float xr = v.x - hr, xi = v.y - hi;
+                        if (hybrid) {                                // B side: (lo, hi) = (even, odd) bf16 k
+                            xr = __uint_as_float(pack_bf16(xr, hr));
+                            xi = __uint_as_float(pack_bf16(xi, hi));
+                        }
+                        float* o = base + t * Kp + q;
+                        o[0] = hr;
+                        o[plane] = hi;
+                        o[2 * plane] = xr;
+                        o[3 * plane] = xi;
                     }
                 }
             }
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                if (r0 + r < rem) {
-                    out[(f * L + Lm + r0 + r) * ldo + t] = make_float2(accr[r], acci[r]);
-                    psum[r] = fmaf(accr[r], accr[r], fmaf(acci[r], acci[r], psum[r]));
+        }
+        // tail rows: thread (r, t) = (tid / 32 + 8 k, tid % 32)
+        for (int r = ty; r < rem; r += 8) {
+            const long long t = t0 + tx;
+            float ar = 0.f, ai = 0.f;
+            for (int q = 0; q < Q; ++q) {
+                const float2 a = sA[r][q];
+                const float2 x = tile[q][tx];
+                ar = fmaf(a.x, x.x, ar);
+                ar = fmaf(-a.y, x.y, ar);
+                ai = fmaf(a.x, x.y, ai);
+                ai = fmaf(a.y, x.x, ai);
+            }
+            if (t < T) {
+                out[(f * L + Lm + r) * ldo + t] = make_float2(ar, ai);
+                if (power) {
+                    float p = ar * ar + ai * ai;
+                    for (int off = 16; off; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
+                    if (tx == 0) spow[r] += p;                       // row r is always handled by the same warp
                 }
-            }
-        }
-        if (power) {                                                 // block reduction of sum_t |q|^2 per row
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                float p = psum[r];
-                for (int off = 16; off; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
-                if ((threadIdx.x & 31) == 0) spow[threadIdx.x >> 5][r] = p;
-            }
-            __syncthreads();
-            if (threadIdx.x < RMAX && r0 + threadIdx.x < rem) {
+            } else if (power) {
                 float p = 0.f;
-                for (int w = 0; w < 8; ++w) p += spow[w][threadIdx.x];
-                power[f * L + Lm + r0 + threadIdx.x] = p / (float)T;
+                for (int off = 16; off; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
             }
-            __syncthreads();
         }
+    }
+    (void)psum;
+    if (power && rem > 0) {
+        __syncthreads();
+        if (threadIdx.x < rem) power[f * L + Lm + threadIdx.x] = spow[threadIdx.x] / (float)T;
     }
 }
 
@@ -662,20 +668,19 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) return SFA_ERR_UNSUPPORTED;
     const int Kp = (int)ceil_div(Q, 4) * 4;
-    {
-        const long long tiles = nf * ceil_div(T, 32) * ceil_div(Kp, 32);
-        long long blocks = tiles;
-        const long long cap = (long long)sm_count() * 8;
-        if (blocks > cap) blocks = cap;
-        prof_aux_begin(st);
-        x_split_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, nf, (int)Q, T, Kp, hybrid, Xs);
-        prof_aux_end(st);
-        SFA_LAUNCH_CHECK();
-    }
     // look directions beyond the last full 128-row tile: few of them -> CUDA-core tail kernel (no ragged tile, no ghost CTA)
     const long long rem = L % kTileL;
     const bool tail = rem > 0 && rem <= kTailMaxRows && L > kTileL;
     const long long Lmain = tail ? L - rem : L;
+    {
+        const int Kh = (int)ceil_div(Q, 8) * 4;
+        const float4* g2_last = reinterpret_cast<const float4*>(G2) + (size_t)(Lmain / kTileL) * Cd * Kh * kTileL;
+        prof_aux_begin(st);
+        x_split_tail_kernel<<<(unsigned)nf, 256, 0, st>>>(X, (int)Q, T, Kp, hybrid, Xs, g2_last, Cd, Kh, d, out, L, Lmain,
+                                                          tail ? (int)rem : 0, ldo, power);
+        prof_aux_end(st);
+        SFA_LAUNCH_CHECK();
+    }
     CUtensorMap xmap, omap;
     {
         cuuint64_t gdim[3] = {(cuuint64_t)Q, (cuuint64_t)T, (cuuint64_t)(4 * nf)};
@@ -760,13 +765,6 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
         return SFA_ERR_CUDA;
     }
     SFA_LAUNCH_CHECK();
-    if (tail) {
-        const float4* g2_last = prm.G2 + (size_t)(Lmain / kTileL) * Cd * prm.Kh * kTileL;
-        const size_t tsmem = (size_t)rem * 2 * prm.Kh * sizeof(float2);
-        pwd_tail_rows_kernel<8><<<(unsigned)nf, 256, tsmem, st>>>(g2_last, Cd, prm.Kh, d, X, (int)Q, T, out, L, Lmain,
-                                                                   (int)rem, ldo, power);
-        SFA_LAUNCH_CHECK();
-    }
     return SFA_OK;
 }
 

@@ -107,7 +107,9 @@ def _radial(kind, N, k, r, rs, setup, replace_zeros, method=None, a0=0.0, check=
                                          int(bool(replace_zeros)), mid, float(a0), _lib.ptr(bn), _lib.ptr(dn),
                                          _lib.ptr(hn), _lib.ptr(status), _lib.ptr(work), _lib.stream_ptr(dev)))
     if replace_zeros:
-        if check == "defer":
+        if check == "none":
+            pass                                      # graph capture / caller reads `status` itself
+        elif check == "defer":
             # queue this call's status FIRST: an error of an earlier call raised by flush() must not
             # lose it (the kernel has already been launched and its result is valid)
             _deferred.add(status)
@@ -174,7 +176,8 @@ def radial_filters(N, k, r, setup, a0, method, kind="spherical_pw", rs=0.0, repl
     pass (the inverse never makes a separate trip through HBM).  Returns (bn, dn, hn), squeezed.
     Equivalent reference sequence: modal_beamforming_rigid_spherical_array.py:34-35.
     ``check="defer"`` keeps the call asynchronous: the "Could not replace zero value" check is
-    validated later (next radial call or ``check_deferred()``) instead of synchronising now."""
+    validated later (next radial call or ``check_deferred()``) instead of synchronising now;
+    ``check="none"`` skips it (CUDA-graph capture: the same inputs were validated once before)."""
     if kind not in _KINDS:
         raise ValueError("unknown radial function: %r" % (kind,))
     kk = asarray_1d(k)

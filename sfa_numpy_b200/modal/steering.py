@@ -295,14 +295,48 @@ class PwdHost:
         self.out_shape = (F, Y_look.shape[0], int(T))
         self._pinned = []
 
-    def pinned_empty(self, shape):
+    def set_operators(self, Y_look, dn, Y_mic):
+        """Replace the resident operators.  CUDA tensors (the outputs of `angular.sht_matrix` /
+        `radial.radial_filters`) are copied device to device; NumPy arrays go through the host path."""
+        if all(isinstance(a, torch.Tensor) and a.is_cuda for a in (Y_look, dn, Y_mic)):
+            Y_look, dn, Y_mic = (as_complex_tensor(a, a.device) for a in (Y_look, dn, Y_mic))
+            dev = Y_look.device
+            with torch.cuda.device(dev):
+                _lib.check(self.lib.sfa_pwd_host_set_operators_dev(self.ctx, _lib.ptr(Y_look), _lib.ptr(Y_mic),
+                                                                   _lib.ptr(dn), _lib.stream_ptr(dev)))
+            return
+        Y_look = np.ascontiguousarray(Y_look, dtype=np.complex128)
+        Y_mic = np.ascontiguousarray(Y_mic, dtype=np.complex128)
+        dn = np.ascontiguousarray(dn, dtype=np.complex128)
+        _lib.check(self.lib.sfa_pwd_host_set_operators(self.ctx, Y_look.ctypes.data, Y_mic.ctypes.data, dn.ctypes.data))
+
+    def pinned_empty(self, shape, dtype=None):
         """Page-locked NumPy array (cudaHostAlloc) for X / out: makes the copies asynchronous."""
-        n = int(np.prod(shape)) * np.dtype(self.np_dtype).itemsize
+        dt = np.dtype(self.np_dtype if dtype is None else dtype)
+        n = int(np.prod(shape)) * dt.itemsize
         p = ctypes.c_void_p()
         _lib.check(self.lib.sfa_host_alloc(ctypes.byref(p), max(n, 1)))
         self._pinned.append(p)
         buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
-        return np.frombuffer(buf, dtype=self.np_dtype, count=int(np.prod(shape))).reshape(shape)
+        return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    def power_map(self, X, power=None, out=None):
+        """Beam power map mean_t |q|^2 ([F, L] float32) through the host path; the beams themselves are only
+        copied back when `out` is given."""
+        X = np.ascontiguousarray(X, dtype=self.np_dtype)
+        if X.ndim == 2:
+            X = X[:, :, None]
+        if X.shape != self.in_shape:
+            raise ValueError("X must have shape {}".format(self.in_shape))
+        if power is None:
+            power = np.empty(self.out_shape[:2], dtype=np.float32)
+        elif power.shape != self.out_shape[:2] or power.dtype != np.float32 or not power.flags.c_contiguous:
+            raise ValueError("power must be a C-contiguous float32 array of shape {}".format(self.out_shape[:2]))
+        if out is not None and (out.shape != self.out_shape or out.dtype != self.np_dtype or not out.flags.c_contiguous):
+            raise ValueError("out must be a C-contiguous {} array of shape {}".format(self.np_dtype, self.out_shape))
+        _lib.check(self.lib.sfa_pwd_host_run_power(self.ctx, X.ctypes.data, out.ctypes.data if out is not None else None,
+                                                   power.ctypes.data))
+        return power
 
     def __call__(self, X, out=None):
         X = np.ascontiguousarray(X, dtype=self.np_dtype)
