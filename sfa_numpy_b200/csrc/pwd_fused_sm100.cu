@@ -47,7 +47,7 @@ constexpr int kMaxK = 64;                           // microphones (complex k) r
 #endif
 constexpr int kStages = SFA_FUSED_STAGES;
 #ifndef SFA_FUSED_PREFETCH
-#define SFA_FUSED_PREFETCH 2
+#define SFA_FUSED_PREFETCH 0
 #endif
 constexpr int kPrefetch = SFA_FUSED_PREFETCH;       // L2 prefetch distance of the spectra stream, in frame tiles
 constexpr int kTailMaxRows = 16;                    // L mod 128 up to this many rows goes to the CUDA-core tail kernel
@@ -189,8 +189,8 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         stage = 0;
                         phase ^= 1;
                     }
-                    // L2 prefetch of the tile kPrefetch steps ahead (the ten clusters working on a bin reach a new
-                    // frame tile together, so without it every one of them waits out a DRAM miss)
+                    // optional L2 prefetch of the tile kPrefetch steps ahead.  Measured on the headline shape: 2 or 4
+                    // tiles ahead cost 3-5 % (the prefetch requests compete with the store stream), so it is off.
                     if (kPrefetch > 0) {
                         int ptt = tt + kPrefetch;
                         long long pgrp = grp;

@@ -68,6 +68,71 @@ def all_gather_slabs(q_loc, F, group=None):
     return torch.cat([buf[r * big: r * big + sizes[r]] for r in range(world)], dim=0)
 
 
+class OverlappedPwd:
+    """Strong-scaled plane-wave decomposition of ONE [F]-bin problem with the complex beams gathered on every
+    rank, the collective hidden behind the compute.
+
+    The bins are dealt out block-cyclically: piece c of rank r is the bin block
+    ``[(c * world + r) * cb, ... + cb)`` with ``cb = F / (world * pieces)``.  Rank r computes its block of piece c
+    straight into its place in the full ``[F, L, T]`` tensor; as soon as that kernel has finished (event on the
+    compute stream) the in-place ``all_gather_into_tensor`` of piece c -- one contiguous ``[world * cb, L, ld]``
+    slab -- runs on a communication stream while piece c + 1 is being computed.  Every GPU has to ingest
+    (world - 1) / world of the output over NVLink, so for the HBM-bound configs the gather, not the compute,
+    sets the time; the overlap hides the smaller of the two.
+
+    `compute(plan, X_piece, out_piece)` may be injected (the CPU/gloo test of the scheduling logic does)."""
+
+    def __init__(self, Y_look, dn, Y_mic, T, pieces=4, precision="c64_fast", form="auto", group=None, make_plan=None,
+                 device=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        F = dn.shape[0]
+        if F % (self.world * pieces):
+            raise ValueError("F = {} must be a multiple of world * pieces = {}".format(F, self.world * pieces))
+        self.pieces, self.cb, self.F, self.T = int(pieces), F // (self.world * pieces), F, int(T)
+        self.dn = dn
+        L = Y_look.shape[0]
+        if make_plan is None:
+            from .modal import steering
+            self.plan = steering.PwdPlan(Y_look, dn[: self.cb], Y_mic, T, precision=precision, form=form, device=device)
+            dev, cdtype, ld = self.plan.dev, self.plan.cdtype, steering._padded_pitch(int(T))
+        else:
+            self.plan, dev, cdtype, ld = make_plan(Y_look, dn[: self.cb], Y_mic, T)
+        self.buf = torch.empty((F, L, ld), dtype=cdtype, device=dev)          # row-padded; gathered with its padding
+        self.full = self.buf[:, :, : self.T]
+        self.comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+
+    def block_start(self, piece, rank=None):
+        return (piece * self.world + (self.rank if rank is None else rank)) * self.cb
+
+    def my_bins(self):
+        """Global bin indices of this rank, in the order its X must be laid out ([pieces * cb, Q, T])."""
+        return [self.block_start(c) + i for c in range(self.pieces) for i in range(self.cb)]
+
+    def __call__(self, X_loc):
+        cb, W = self.cb, self.world
+        for c in range(self.pieces):
+            f0 = self.block_start(c)
+            self.plan.dn = self.dn[f0:f0 + cb]
+            self.plan(X_loc[c * cb:(c + 1) * cb], out=self.full[f0:f0 + cb])
+            if W == 1:
+                continue
+            slab = self.buf[c * W * cb:(c + 1) * W * cb]
+            mine = self.buf[f0:f0 + cb]
+            if self.comm is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                self.comm.wait_event(ev)
+                with torch.cuda.stream(self.comm):
+                    dist.all_gather_into_tensor(_as_real(slab), _as_real(mine), group=self.group)
+            else:                                                              # CPU tests (gloo): no in-place aliasing
+                dist.all_gather_into_tensor(_as_real(slab), _as_real(mine.clone()), group=self.group)
+        if self.comm is not None and W > 1:
+            torch.cuda.current_stream().wait_stream(self.comm)
+        return self.full
+
+
 def gather_power_map(q_loc, F, group=None, reduce=None):
     """Frame-averaged beam power map mean_t |q|^2, [F, L] float32, gathered on every rank: the
     cheap collective when only the map (not the beam signals) is needed downstream.  The local

@@ -68,3 +68,54 @@ def test_gloo_world2(F):
     results = mgr.dict()
     mp.spawn(_worker, args=(2, port, F, results), nprocs=2, join=True)
     assert results.get(0) and results.get(1)
+
+
+class _TorchPlan:
+    """Stand-in for steering.PwdPlan in the CPU test of OverlappedPwd's scheduling (block-cyclic pieces,
+    in-place slab all-gather): same call signature, plain torch arithmetic."""
+
+    def __init__(self, Y_look, dn, Y_mic, T):
+        self.Y_look, self.Y_mic, self.dn = Y_look, Y_mic, dn
+
+    def __call__(self, X, out=None):
+        out.copy_(_torch_pwd(self.Y_look, self.dn, self.Y_mic, X))
+        return out
+
+
+def _overlap_worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(1)
+        F, L, M, Q, T, pieces = 12, 5, 4, 3, 6, 3
+        Y_look = torch.randn(L, M, dtype=torch.complex128, generator=g)
+        Y_mic = torch.randn(Q, M, dtype=torch.complex128, generator=g)
+        dn = torch.randn(F, M, dtype=torch.complex128, generator=g)
+        X = torch.randn(F, Q, T, dtype=torch.complex128, generator=g)
+        full = _torch_pwd(Y_look, dn, Y_mic, X)
+        op = sd.OverlappedPwd(Y_look, dn, Y_mic, T, pieces=pieces,
+                              make_plan=lambda yl, d, ym, t: (_TorchPlan(yl, d, ym, t), torch.device("cpu"),
+                                                              torch.complex128, t + 2))
+        bins = op.my_bins()
+        assert len(bins) == F // world and len(set(bins)) == len(bins)
+        got = op(X[bins])
+        assert got.shape == full.shape and torch.allclose(got, full)
+        # every bin is owned by exactly one rank
+        owners = [None] * world
+        dist.all_gather_object(owners, bins)
+        assert sorted(b for o in owners for b in o) == list(range(F))
+        with pytest.raises(ValueError):
+            sd.OverlappedPwd(Y_look, dn[:10], Y_mic, T, pieces=pieces, make_plan=lambda *a: None)
+        results[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_pwd_gloo_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_overlap_worker, args=(2, port, results), nprocs=2, join=True)
+    assert results.get(0) and results.get(1)
