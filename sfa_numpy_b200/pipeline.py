@@ -15,6 +15,7 @@ tracing compiler: the kernels are the hand-written ones, the graph only removes 
 """
 import torch
 
+from . import _lib
 from .modal import angular, radial, steering
 from .util import _device_of
 
@@ -57,7 +58,10 @@ class ModalBeamformer:
         self.plan = steering.PwdPlan(Y_q, dn[self.bins[0]:self.bins[1]], Y_p, self.T, precision=precision, device=dev)
         self.graph = None
         self.graph_error = None
+        lib = _lib.load()
+        n0 = lib.sfa_launch_count()
         self._eager()
+        self.launches_per_run = int(lib.sfa_launch_count() - n0)     # kernels per step (eager or replayed)
         if graph:
             self._capture()
 
