@@ -148,6 +148,13 @@ int sfa_norm_of_columns(int64_t M, int64_t N, const sfa_c128* A, double p, doubl
 int sfa_coherence_of_columns(int64_t M, int64_t N, const sfa_c128* A, double* norms, double* result,
                              void* stream);
 
+/* angular.grid_equal_angle (kind 0, angular.py:153-185), grid_gauss (kind 1, angular.py:188-214),
+ * grid_equal_polar_angle (kind 2, angular.py:217-235) on the device.  sfa_grid_points gives the number of
+ * sampling points ((2n+2)^2, (n+1)(2n+2), 2n+1; -1 for bad arguments); azi / colat / weights are device
+ * arrays of that many doubles in the reference's order (colat is not written for kind 2). */
+int64_t sfa_grid_points(int kind, int n);
+int sfa_grid(int kind, int n, double* azi, double* colat, double* weights, void* stream);
+
 /* ---- stage 3: plane-wave decomposition / steering ------------------------------ */
 
 /* q_f = Y_L * diag(d_f) * Y_Q^H * X_f   for every bin f  -- the example idiom

@@ -3,6 +3,7 @@
 //   sfa_matdiagmul        <- util.matdiagmul                micarray/util.py:65-93
 //   sfa_norm_of_columns   <- util.norm_of_columns           micarray/util.py:5-21
 //   sfa_coherence_of_columns <- util.coherence_of_columns   micarray/util.py:24-45
+//   sfa_grid              <- angular.grid_equal_angle / grid_gauss / grid_equal_polar_angle   angular.py:153-235
 #include "sfa_common.cuh"
 
 namespace sfa {
@@ -23,6 +24,79 @@ __global__ void legendre_matrix_kernel(int N, long long Q, const double* __restr
             pm = p;
             p = pn;
             L[(long long)(n + 1) * Q + q] = make_double2((2 * n + 3) * inv4pi * pn, 0.0);
+        }
+    }
+}
+
+// Sampling grids (angular.py:153-235), one thread per point.
+//   kind 0  grid_equal_angle(n):  (2n+2)^2 points, azi = j * 2pi/(2n+2), colat = (i + 1/2) * pi/(2n+2) (np.linspace
+//           arithmetic reproduced: i * step, then + step/2), weights 2pi/(n+1) sin(th) sum_{p odd} sin(p th)/p / (n+1)
+//   kind 1  grid_gauss(n):        (n+1)(2n+2) points, colat = arccos of the Gauss-Legendre nodes of order n+1 in
+//           ascending x (np.polynomial.legendre.leggauss order), weights w_i * pi/(n+1).  Nodes by Newton on the
+//           three-term recurrence from the Chebyshev-like guess, weights 2 / ((1 - x^2) P'(x)^2): both at rounding level.
+//   kind 2  grid_equal_polar_angle(n): 2n+1 points on the circle, weights 1/(2n+1); colat is not written.
+// Layout of the outputs as in the reference: azi = np.tile(azi, rows), colat/weights = np.repeat(., 2n+2).
+__device__ double gauss_node(int m, int i, double* weight) {
+    const double kPi = 3.14159265358979323846;
+    // nodes ascending in x: the i-th smallest root of P_m
+    double x = -cos(kPi * (i + 0.75) / (m + 0.5));
+    double dp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+        double p0 = 1.0, p1 = x;
+        for (int k = 1; k < m; ++k) {
+            const double p2 = ((2 * k + 1) * x * p1 - k * p0) / (k + 1);
+            p0 = p1;
+            p1 = p2;
+        }
+        if (m == 0) p1 = 1.0;
+        dp = m * (x * p1 - p0) / (x * x - 1.0);
+        const double dx = p1 / dp;
+        x -= dx;
+        if (fabs(dx) <= 1e-16 * fmax(fabs(x), 1e-300) || (it > 3 && fabs(dx) < 4e-16)) break;
+    }
+    // derivative at the converged node
+    {
+        double p0 = 1.0, p1 = x;
+        for (int k = 1; k < m; ++k) {
+            const double p2 = ((2 * k + 1) * x * p1 - k * p0) / (k + 1);
+            p0 = p1;
+            p1 = p2;
+        }
+        dp = m * (x * p1 - p0) / (x * x - 1.0);
+    }
+    *weight = 2.0 / ((1.0 - x * x) * dp * dp);
+    return x;
+}
+
+__global__ void grid_kernel(int kind, int n, double* __restrict__ azi, double* __restrict__ colat,
+                            double* __restrict__ weights) {
+    const double kPi = 3.14159265358979323846;
+    const int m = 2 * n + 2;
+    const long long total = kind == 0 ? (long long)m * m : kind == 1 ? (long long)(n + 1) * m : 2 * n + 1;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        if (kind == 2) {
+            const int num = 2 * n + 1;
+            const double step = (2 * kPi) / num;
+            azi[idx] = idx * step;
+            weights[idx] = 1.0 / num * 1.0;
+            continue;
+        }
+        const int i = (int)(idx / m), j = (int)(idx - (long long)i * m);      // row (colatitude), column (azimuth)
+        const double astep = (2 * kPi) / m;
+        azi[idx] = j * astep;
+        if (kind == 0) {
+            const double cstep = kPi / m;
+            const double th = i * cstep + cstep / 2;
+            double s = 0.0;
+            for (int p = 1; p < m; p += 2) s += sin(p * th) / p;
+            colat[idx] = th;
+            weights[idx] = 2 * kPi / (n + 1) * sin(th) * s / (n + 1);
+        } else {
+            double wgt;
+            const double x = gauss_node(n + 1, i, &wgt);
+            colat[idx] = acos(x);
+            weights[idx] = wgt * (kPi / (n + 1));
         }
     }
 }
@@ -140,6 +214,21 @@ extern "C" int sfa_legendre_matrix(int N, int64_t Q, const double* ctheta, sfa_c
     if (Q == 0) return SFA_OK;
     if (!ctheta || !L) return SFA_ERR_INVALID;
     legendre_matrix_kernel<<<grid_for(Q, 256), 256, 0, (cudaStream_t)stream>>>(N, Q, ctheta, reinterpret_cast<double2*>(L));
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
+
+extern "C" int64_t sfa_grid_points(int kind, int n) {
+    if (n < 0 || kind < 0 || kind > 2) return -1;
+    const int64_t m = 2 * (int64_t)n + 2;
+    return kind == 0 ? m * m : kind == 1 ? ((int64_t)n + 1) * m : 2 * (int64_t)n + 1;
+}
+
+extern "C" int sfa_grid(int kind, int n, double* azi, double* colat, double* weights, void* stream) {
+    const int64_t P = sfa_grid_points(kind, n);
+    if (P < 0) return SFA_ERR_INVALID;
+    if (!azi || !weights || (kind != 2 && !colat)) return SFA_ERR_INVALID;
+    grid_kernel<<<grid_for(P, 128), 128, 0, (cudaStream_t)stream>>>(kind, n, azi, colat, weights);
     SFA_LAUNCH_CHECK();
     return SFA_OK;
 }

@@ -71,6 +71,38 @@ constexpr int kStoreBoxBytes = 32 * 128;            // 32 rows x 16 frames (128 
 #define SFA_FUSED_RING 2
 #endif
 constexpr int kStoreRing = SFA_FUSED_RING;          // staging slots (one pass = 2 boxes = 8 KB each) per epilogue warp
+// L2 policies (createpolicy + .L2::cache_hint).  When the beam tensor is much larger than L2 its stores carry
+// evict_first: written lines are never read again by this kernel, and without the hint they push the
+// group-product table and the spectra planes (both re-read by every task of a bin) out of L2 -- measured on the
+// headline shape: 4.99 -> 4.64 ms per step.  (evict_last on the table loads alone gives 4.72 ms and adds
+// nothing on top; a third staging slot per epilogue warp costs 4 %.)
+#ifndef SFA_FUSED_G2_HINT
+#define SFA_FUSED_G2_HINT 0
+#endif
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* map, const void* src, int c0, int c1, int c2,
+                                                  uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+                 : "memory");
+}
 constexpr int kStoreWarpBytes = kStoreRing * 2 * kStoreBoxBytes;
 
 struct Params {
@@ -85,6 +117,7 @@ struct Params {
     int ltiles, lt_groups, csize, t_tiles;
     long long groups;            // F * lt_groups
     float* power;                // nullable: [F][L] mean_t |q|^2, accumulated in the epilogue (a CTA owns whole rows)
+    int store_evict_first;       // beam stores with the L2 evict_first policy (output much larger than L2)
     int debug;                   // timing attribution (SFA_DEBUG_HOOKS builds only): 1 no TMA stores, 2 no build FMAs,
                                  // 4 no staging writes, 8 no MMAs, 16 no operand loads
 };
@@ -314,6 +347,9 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         int npairs = prm.Kh - half * 16;
         npairs = npairs < 0 ? 0 : (npairs > 16 ? 16 : npairs);
         uint32_t a_phase = 0;
+#if SFA_FUSED_G2_HINT
+        const uint64_t g2_pol = l2_policy_evict_last();
+#endif
         for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
             long long f;
             int lt;
@@ -335,7 +371,11 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     float4 v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
+#if SFA_FUSED_G2_HINT
+                        v[j] = (j < npairs) ? ldg_hint(gg + (size_t)j * kTileL, g2_pol) : make_float4(0.f, 0.f, 0.f, 0.f);
+#else
                         v[j] = (j < npairs) ? __ldg(gg + (size_t)j * kTileL) : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         are[2 * j] = fmaf(dg[g].x, v[j].x, are[2 * j]);
@@ -390,6 +430,8 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         const uint32_t sw = (uint32_t)(lane & 7);
         int acc = 0, buf = 0;
         uint32_t acc_phase = 0;
+        const uint64_t st_pol = l2_policy_evict_first();
+        const bool st_hint = prm.store_evict_first != 0;
         for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
             long long f;
             int lt;
@@ -444,9 +486,15 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0 && !(prm.debug & 1)) {
-                        tma_store_3d(&o_map, sbuf, (int)(2 * t0), l0, (int)f, false);
-                        if (t0 + 16 < prm.T)
-                            tma_store_3d(&o_map, sbuf + kStoreBoxBytes, (int)(2 * (t0 + 16)), l0, (int)f, false);
+                        if (st_hint) {
+                            tma_store_3d_hint(&o_map, sbuf, (int)(2 * t0), l0, (int)f, st_pol);
+                            if (t0 + 16 < prm.T)
+                                tma_store_3d_hint(&o_map, sbuf + kStoreBoxBytes, (int)(2 * (t0 + 16)), l0, (int)f, st_pol);
+                        } else {
+                            tma_store_3d(&o_map, sbuf, (int)(2 * t0), l0, (int)f, false);
+                            if (t0 + 16 < prm.T)
+                                tma_store_3d(&o_map, sbuf + kStoreBoxBytes, (int)(2 * (t0 + 16)), l0, (int)f, false);
+                        }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     if (++buf == kStoreRing) buf = 0;
@@ -724,6 +772,7 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     prm.t_tiles = (int)ceil_div(T, kTileT);
     prm.groups = nf * prm.lt_groups;
     prm.power = power;
+    prm.store_evict_first = ((double)nf * (double)L * (double)ldo * 8.0 > 256e6) ? 1 : 0;     // >> L2 (126 MB)
 #ifdef SFA_DEBUG_HOOKS
     prm.debug = options().fused_debug;
 #else

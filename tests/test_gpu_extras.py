@@ -80,3 +80,30 @@ def test_power_map():
             assert np.max(np.abs(pm - ref) / ref) < 2e-6
     with pytest.raises(ValueError):
         S.power_map(torch.zeros((2, 2, 2), dtype=torch.complex64))
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 8, 16, 32, 60])
+def test_grids_on_device(n):
+    """angular.grid_* with device= (sfa_grid kernel) against the reference's NumPy formulas
+    (angular.py:153-235; oracle restatement, golden-pinned) -- FP64, 1e-13 absolute on angles and weights."""
+    import torch
+    import sfa_numpy_b200 as micarray
+    A = micarray.modal.angular
+    for name, ref in (("grid_equal_angle", O.grid_equal_angle(n)), ("grid_gauss", O.grid_gauss(n))):
+        got = getattr(A, name)(n, device="cuda")
+        assert len(got) == 3
+        for g, r in zip(got, ref):
+            assert g.is_cuda and g.dtype == torch.float64 and tuple(g.shape) == r.shape
+            np.testing.assert_allclose(g.cpu().numpy(), r, rtol=0, atol=2e-13)
+        assert abs(float(got[2].sum()) - 4 * np.pi) < 1e-11
+    pol, w = A.grid_equal_polar_angle(n, device="cuda")
+    num = 2 * n + 1
+    np.testing.assert_array_equal(pol.cpu().numpy(), np.linspace(0, 2 * np.pi, num=num, endpoint=False))
+    np.testing.assert_array_equal(w.cpu().numpy(), np.ones(num) / num)
+    # the host flavour is unchanged and the device grids feed sht_matrix directly
+    azi, colat, wt = A.grid_gauss(n, device="cuda")
+    Y = A.sht_matrix(n, azi, colat, wt)
+    Yh = O.sht_matrix(n, *O.grid_gauss(n))
+    assert float(np.max(np.abs(Y.cpu().numpy() - Yh))) < 1e-12
+    with pytest.raises(ValueError):
+        A.grid_gauss(-1, device="cuda")
