@@ -862,7 +862,9 @@ def scaling_variants(torch, dist, sdist, S, bf, timed, world, rank, dev, args, c
       allgather_power_map     -- + NCCL all-gather of the [F/N, L] float32 beam power maps (cfg 3: this is `value`);
       allgather_complex_beams -- the complex beam tensor [F, L, T] gathered on every rank, the bins dealt out
                                  block-cyclically so that the gather of block c overlaps the compute of block c + 1
-                                 (`dist.OverlappedPwd`).  Every GPU ingests (N-1)/N of the output over NVLink."""
+                                 (`dist.OverlappedPwd`).  Every GPU ingests (N-1)/N of the output over NVLink.
+                                 Two transports: NCCL all-gather per block on a side stream, and (`_p2p`) DMA pushes
+                                 of the finished block into every peer's buffer (CUDA IPC, copy engines, no SMs)."""
     import sfa_numpy_b200 as micarray
     from oracle import sfa_oracle as O
     F, L, T, Q = cfg["F"], cfg["L"], cfg["T"], cfg["Q"]
@@ -877,26 +879,30 @@ def scaling_variants(torch, dist, sdist, S, bf, timed, world, rank, dev, args, c
     while F % (world * pieces) and pieces > 1:
         pieces -= 1
     if F % (world * pieces) == 0:
-        op = sdist.OverlappedPwd(bf.Y_look, bf.dn, bf.Y_mic, T, pieces=pieces, precision=args.precision, device=dev)
-        mine = op.my_bins()
         Xfull = O.synth_spectra(F, Q, T, seed=0)
-        X_bc = torch.from_numpy(np.ascontiguousarray(Xfull[mine])).to(dev)
-        del Xfull
-
-        def step_ii():
-            bf._stage12(check="none")              # stages 1-2 as in the other variants (eager launches)
-            op(X_bc)
-        ms_ii = timed(step_ii, n=3)
-        # result check: this rank's slab of the gathered tensor against its own resident result
-        full = op.full
         nbk = bf.out.shape[0]
-        same = bool(torch.equal(full[f0:f0 + nbk], bf.out))
-        ingest = 8.0 * F * L * op.buf.shape[2] * (world - 1) / world
-        row["allgather_complex_beams"] = {"ms": ms_ii, "outputs_per_s": outputs / (ms_ii * 1e-3), "pieces": pieces,
-                                          "ingest_bytes_per_gpu": ingest, "ingest_GBps_per_gpu": ingest / (ms_ii * 1e-3) / 1e9,
-                                          "matches_resident_slab": same}
-        del op, X_bc, full
-        torch.cuda.empty_cache()
+        for transport, key in (("nccl", "allgather_complex_beams"), ("p2p", "allgather_complex_beams_p2p")):
+            try:
+                op = sdist.OverlappedPwd(bf.Y_look, bf.dn, bf.Y_mic, T, pieces=pieces, precision=args.precision, device=dev,
+                                         transport=transport)
+                X_bc = torch.from_numpy(np.ascontiguousarray(Xfull[op.my_bins()])).to(dev)
+
+                def step_ii():
+                    bf._stage12(check="none")              # stages 1-2 as in the other variants (eager launches)
+                    op(X_bc)
+                ms_ii = timed(step_ii, n=3)
+                # result check: this rank's slab of the gathered tensor against its own resident result
+                same = bool(torch.equal(op.full[f0:f0 + nbk], bf.out))
+                ingest = 8.0 * F * L * op.buf.shape[2] * (world - 1) / world
+                row[key] = {"ms": ms_ii, "outputs_per_s": outputs / (ms_ii * 1e-3), "pieces": pieces, "transport": transport,
+                            "ingest_bytes_per_gpu": ingest, "ingest_GBps_per_gpu": ingest / (ms_ii * 1e-3) / 1e9,
+                            "matches_resident_slab": same}
+                del op, X_bc
+            except Exception as e:
+                row[key] = {"error": repr(e)}
+                torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+        del Xfull
     res["cfg3"] = row
     # ---- cfg 5 (the config BASELINE.json names for 1/2/4/8 GPUs): tensor-bound, K-loop kernel ----
     try:
@@ -930,14 +936,22 @@ def scaling_variants(torch, dist, sdist, S, bf, timed, world, rank, dev, args, c
         pieces5 = 8
         while F5 % (world * pieces5) and pieces5 > 1:
             pieces5 -= 1
-        op5 = sdist.OverlappedPwd(Y_q, dn, Y_p, T5, pieces=pieces5, precision=args.precision, device=dev)
-        X5bc = X5[op5.my_bins()].contiguous()
-        ms_c = timed(lambda: op5(X5bc), n=3)
-        ingest5 = 8.0 * F5 * L5 * op5.buf.shape[2] * (world - 1) / world
-        row5["allgather_complex_beams"] = {"ms": ms_c, "outputs_per_s": outputs5 / (ms_c * 1e-3), "pieces": pieces5,
-                                           "ingest_bytes_per_gpu": ingest5, "ingest_GBps_per_gpu": ingest5 / (ms_c * 1e-3) / 1e9}
+        for transport, key in (("nccl", "allgather_complex_beams"), ("p2p", "allgather_complex_beams_p2p")):
+            try:
+                op5 = sdist.OverlappedPwd(Y_q, dn, Y_p, T5, pieces=pieces5, precision=args.precision, device=dev,
+                                          transport=transport)
+                X5bc = X5[op5.my_bins()].contiguous()
+                ms_c = timed(lambda: op5(X5bc), n=3)
+                ingest5 = 8.0 * F5 * L5 * op5.buf.shape[2] * (world - 1) / world
+                row5[key] = {"ms": ms_c, "outputs_per_s": outputs5 / (ms_c * 1e-3), "pieces": pieces5, "transport": transport,
+                             "ingest_bytes_per_gpu": ingest5, "ingest_GBps_per_gpu": ingest5 / (ms_c * 1e-3) / 1e9}
+                del op5, X5bc
+            except Exception as e:
+                row5[key] = {"error": repr(e)}
+                torch.cuda.synchronize()
+            torch.cuda.empty_cache()
         res["cfg5"] = row5
-        del op5, X5, X5bc
+        del X5
         torch.cuda.empty_cache()
     except Exception as e:
         res["cfg5"] = {"error": repr(e)}

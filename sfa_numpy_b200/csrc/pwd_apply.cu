@@ -34,7 +34,7 @@ size_t cgemm3x_kloop_scratch_bytes(long long K, int hybrid);
 // fused steering kernel (pwd_fused_sm100.cu): A_f built in tensor memory, one persistent launch
 bool pwd_fused_supported(long long L, long long Q, long long T, int Cd, long long out_ld, const void* out);
 size_t pwd_fused_g2_bytes(long long L, long long Q, int Cd);
-size_t pwd_fused_xs_bytes(long long nf, long long Q, long long T);
+size_t pwd_fused_xs_bytes(long long nf, long long L, long long Q, long long T);
 int launch_group_products_g2(const double2* YL, const double2* YQt, long long L, long long Q, int M, int Cd,
                              int per_order, float* G2, cudaStream_t st);
 int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd, const float* G2, const float2* d,
@@ -510,7 +510,7 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
         p->off_dF = off;
         off += align_up((size_t)fc * s->Cd * 8);
         p->off_Xs = off;                                      // pre-split spectra [fc][4][T][Kp]
-        off += align_up(pwd_fused_xs_bytes(fc, s->Q, s->T));
+        off += align_up(pwd_fused_xs_bytes(fc, s->L, s->Q, s->T));
     } else if (form == 1) {
         p->off_YQt = off;                                     // conj(Y_Q)^T for the group products
         off += align_up((size_t)s->M * s->Q * 16);

@@ -69,6 +69,8 @@ struct Options {
     int issuers;           // MMA issuer warps of the resident-K kernel (1 or 2)
     int old_build;         // steering build: generic kernel instead of the few-groups fast kernel
     int no_fused;          // steering form: slab build + GEMM launches instead of the fused persistent kernel
+    int fused_prepass;     // fused kernel: split ALL spectra in the pre-pass kernel (no in-kernel stream-ahead conversion)
+    int fused_D, fused_ring; // stream-ahead distance / plane-ring size of the fused kernel in bins (0 = automatic)
     int fused_debug;       // timing-attribution switches of the fused kernel; honoured by SFA_DEBUG_HOOKS builds only
 };
 Options& options();

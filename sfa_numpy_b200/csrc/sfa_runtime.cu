@@ -42,6 +42,9 @@ static Options make_options() {
     o.issuers = ((int)env_num("SFA_ISSUERS", 1.0) == 2) ? 2 : 1;
     o.old_build = env_flag("SFA_OLD_BUILD");
     o.no_fused = env_flag("SFA_NO_FUSED");
+    o.fused_prepass = env_flag("SFA_FUSED_PREPASS");
+    o.fused_D = (int)env_num("SFA_FUSED_D", 0.0);
+    o.fused_ring = (int)env_num("SFA_FUSED_RING", 0.0);
     o.fused_debug = (int)env_num("SFA_FUSED_DEBUG", 0.0);
     return o;
 }
@@ -187,6 +190,9 @@ static double* option_slot(const char* key, int** islot) {
     else if (!strcmp(key, "issuers")) *islot = &o.issuers;
     else if (!strcmp(key, "old_build")) *islot = &o.old_build;
     else if (!strcmp(key, "no_fused")) *islot = &o.no_fused;
+    else if (!strcmp(key, "fused_prepass")) *islot = &o.fused_prepass;
+    else if (!strcmp(key, "fused_D")) *islot = &o.fused_D;
+    else if (!strcmp(key, "fused_ring")) *islot = &o.fused_ring;
     else if (!strcmp(key, "fused_debug")) *islot = &o.fused_debug;
     return nullptr;
 }

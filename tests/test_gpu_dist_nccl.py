@@ -39,6 +39,16 @@ def _worker(rank, world, port, results):
         got = op(X[op.my_bins()].contiguous())
         torch.cuda.synchronize()
         assert torch.equal(got, single)
+        # (b2) the same with peer-to-peer DMA pushes instead of NCCL (buffers mapped over CUDA IPC), twice (buffer reuse)
+        op2 = sd.OverlappedPwd(Y_q, dn, Y_p, T, pieces=3, precision="c64_fast", transport="p2p")
+        Xbc = X[op2.my_bins()].contiguous()
+        for _ in range(2):
+            op2.full.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            got2 = op2(Xbc)
+            torch.cuda.synchronize()
+            assert torch.equal(got2, single)
         # (c) the power map out of the fused kernel, gathered
         f0, f1 = sd.shard_bins(F, world, rank)
         plan = S.PwdPlan(Y_q, dn[f0:f1], Y_p, T, precision="c64_fast")

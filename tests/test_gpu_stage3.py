@@ -371,3 +371,51 @@ def test_pwd_fused_kernel_shapes(mic, precision):
     ref = O.pwd_factored(Pq, Dn, Pp, X.astype(np.complex128))
     q = S.pwd(Pq, Dn, Pp, torch.from_numpy(X).cuda(), precision=precision, form="steering")
     assert bin_err(cpu(q), ref) < TOL64
+
+
+@pytest.mark.parametrize("precision", ["c64_fast", "c64"])
+def test_pwd_fused_stream_ahead_conversion(mic, precision):
+    """Launches with many bins: the fused kernel's spare warps split the spectra of the bins ahead of the ones
+    being multiplied (hand-over through L2 with release/acquire counters, tail look directions and their power
+    sums on the way).  Same arithmetic as the pre-pass, so the beams must be BIT-identical to a run with
+    `fused_prepass` = 1 (every bin split by the pre-pass kernel), and both must match the oracle on spot bins.
+    Shapes: ghost CTA in the pair (odd tile count), tail rows (L mod 128 <= 16), fewer 32-frame tiles than
+    slices (idle slices), few microphones (padded k), the headline's row geometry."""
+    import torch
+    from sfa_numpy_b200 import _lib
+    A, R, S = mic.modal.angular, mic.modal.radial, mic.modal.steering
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    #        N  Q   L    F    T
+    cases = [(3, 20, 389, 260, 100), (2, 9, 700, 200, 45), (4, 25, 2562, 64, 130), (3, 16, 256, 300, 33),
+             (2, 12, 130, 600, 64)]
+    for (N, Q, L, F, T) in cases:
+        az, co, w = O.fibonacci_grid(Q)
+        azl, col, _ = O.fibonacci_grid(L)
+        Yp_ref, Yq_ref = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
+        k = np.linspace(0.5, 40.0, F)
+        dn_ref, _ = O.regularize(1 / O.spherical_pw(N, k, 0.042, "rigid"), 100, "Tikh")
+        X = (rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(np.complex64)
+        Xd = torch.from_numpy(X).cuda()
+        res = {}
+        for prepass in (0.0, 1.0):
+            try:
+                _lib.check(lib.sfa_set_option(b"fused_prepass", prepass))
+                plan = S.PwdPlan(Yq_ref, dn_ref, Yp_ref, T, precision=precision, form="steering")
+                q1 = plan(Xd, power=True).clone()
+                pm1 = plan.power.clone()
+                for _ in range(3):                           # repeated launches reuse counters and planes
+                    q2 = plan(Xd, power=True)
+                assert torch.equal(q1, q2) and torch.equal(pm1, plan.power), (N, Q, L, F, T, prepass)
+                res[prepass] = (q1, pm1)
+            finally:
+                lib.sfa_set_option(b"fused_prepass", 0.0)
+        assert torch.equal(res[0.0][0], res[1.0][0]), ("beams differ from the pre-pass run", N, Q, L, F, T)
+        pm_a, pm_b = cpu(res[0.0][1]), cpu(res[1.0][1])
+        assert np.max(np.abs(pm_a - pm_b) / np.max(pm_b, axis=1, keepdims=True)) < 1e-6
+        bins = sorted(set([0, 1, F // 3, F // 2, F - 2, F - 1]))
+        ref = O.pwd_factored(Yq_ref, O.repeat_n_m(dn_ref)[bins], Yp_ref, X[bins].astype(np.complex128))
+        got = cpu(res[0.0][0][bins])
+        assert bin_err(got, ref) < TOL64, (N, Q, L, F, T, bin_err(got, ref))
+        pm_ref = np.mean(np.abs(ref) ** 2, axis=2)
+        assert np.max(np.abs(pm_a[bins] - pm_ref) / np.max(pm_ref, axis=1, keepdims=True)) < 1e-5
