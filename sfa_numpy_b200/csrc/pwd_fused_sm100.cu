@@ -723,621 +723,6 @@ __device__ __forceinline__ void convert_slice(const Params& prm, unsigned char* 
 
 template <bool kHybrid>
 __device__ void convert_ahead(const Params& prm, Barriers* bars, unsigned char* smem, int cw, int lane,
-                              long long cluster_id, long long n_clusters, int crank);
-
-struct Params {
-    long long F, L, T;           // bins, look directions handled by this kernel (a multiple of 128 when the tail kernel takes the rest), frames
-    long long Lrows;             // rows per bin of the beam tensor / power map (all look directions)
-    int K;                       // microphones (<= 64)
-    int ksteps, kboxes;          // ceil(K/8), ceil(K/32)
-    int ngroups;                 // columns of d (<= NG)
-    const float4* G2;            // [ltiles][ngroups][Kh][128] : (G[g][l][2j], G[g][l][2j+1]) per lane l
-    int Kh;                      // ksteps * 4 column pairs
-    const float2* d;             // [F][ngroups] complex64
-    int ltiles, lt_groups, csize, t_tiles;
-    long long groups;            // F * lt_groups
-    float* power;                // nullable: [F][L] mean_t |q|^2, accumulated in the epilogue (a CTA owns whole rows)
-    int store_evict_first;       // beam stores with the L2 evict_first policy (output much larger than L2)
-    // stream-ahead conversion of the spectra by the two spare warps of every CTA (conv_D = 0: all done by the pre-pass)
-    int conv_D;                  // task on bin f converts one slice of bin f + conv_D; bins < conv_D come from the pre-pass
-    int nsl;                     // slices per bin = lt_groups * csize (one per CTA-task of a bin)
-    int Q, Kp, rem;              // microphones, padded k extent of the planes, tail look directions (L mod 128 <= 16)
-    const float2* X;             // [F][Q][T] raw spectra
-    float* Xs;                   // [F][4][T][Kp] split planes
-    const float4* G2_last;       // group products of the tail rows
-    float2* out;                 // beam tensor (tail rows are written with plain stores)
-    long long ldo, Lm;           // row pitch of out, first tail row
-    int* ready;                  // [F] slices of the bin converted so far
-    int* done;                   // [F] CTA-tasks of the bin that have received all their planes
-    int ring;                    // plane slots: bin f lives in slot f % ring (conv_D > 0); = F otherwise
-    float* tail_part;            // [F][nsl][16] partial power sums of the tail rows
-    int debug;                   // timing attribution (SFA_DEBUG_HOOKS builds only): 1 no TMA stores, 2 no build FMAs,
-                                 // 4 no staging writes, 8 no MMAs, 16 no operand loads, 32 converters read no X,
-                                 // 64 converters write no planes
-};
-
-struct __align__(8) Barriers {
-    uint64_t b_full[kStages];
-    uint64_t b_empty[kStages];
-    uint64_t acc_full[2];
-    uint64_t acc_empty[2];
-    uint64_t a_full;
-    uint64_t a_empty;
-    uint32_t tmem_base;
-    uint32_t pad;
-};
-
-template <bool kHybrid, int NG>
-__global__ void __launch_bounds__(kThreads, 1)
-pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap o_map,
-                 const Params prm) {
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    unsigned char* stage_base = smem;                                   // kStages x 64 KB
-    unsigned char* store_base = smem + (size_t)kStages * kStageBytes;   // 4 x 16 KB
-    Barriers* bars = reinterpret_cast<Barriers*>(store_base + kEpiWarps * kStoreWarpBytes);
-    unsigned char* conv_base = reinterpret_cast<unsigned char*>(bars) + 256;      // converter warps' tile (conv_D > 0 only)
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int csize = prm.csize;
-    const uint32_t crank = (csize > 1) ? cluster_ctarank() : 0u;
-    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
-    const long long cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&bars->b_full[s], 1);
-            mbar_init(&bars->b_empty[s], csize);        // the MMA issuer of every CTA in the cluster
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&bars->acc_full[a], 1);
-            mbar_init(&bars->acc_empty[a], kEpiWarps);
-        }
-        mbar_init(&bars->a_full, kBuildWarps);
-        mbar_init(&bars->a_empty, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(&bars->tmem_base)),
-                     "r"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    if (csize > 1) cluster_sync_all();
-    tcgen05_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-
-    // group -> (bin f, l-tile of this CTA); a "ghost" l-tile beyond ltiles only keeps the multicast protocol alive
-    auto decode = [&](long long grp, long long& f, int& lt) {
-        f = grp / prm.lt_groups;
-        lt = (int)(grp - f * prm.lt_groups) * csize + (int)crank;
-    };
-
-    // setmaxnreg sits INSIDE each role's branch so that it dominates that role's code only (ptxas sizes the
-    // register allocation of a region by the setmaxnreg that dominates it)
-    if (warp < kEpiWarp0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
-    if (warp == 0) {
-        // ===================== TMA producer: stream the pre-split spectra of the bin =====================
-        if (elect_one_sync()) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&x_map) : "memory");
-            int stage = 0;
-            uint32_t phase = 0;
-            for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
-                const int f = (int)(grp / prm.lt_groups);
-                const int fslot = f % prm.ring;
-                if (prm.conv_D > 0) {
-                    // planes of bin f are written by the converter warps of the CTAs working conv_D bins back
-                    // (the first conv_D bins by the whole grid in its prologue)
-                    while (ld_acquire_gpu(prm.ready + f) < prm.nsl) __nanosleep(64);
-                    asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy writes -> TMA reads
-                }
-                for (int tt = 0; tt < prm.t_tiles; ++tt) {
-                    mbar_wait(&bars->b_empty[stage], phase ^ 1);
-                    unsigned char* dst = stage_base + (size_t)stage * kStageBytes;
-                    if (prm.debug & 16) {
-                        mbar_arrive(&bars->b_full[stage]);
-                        if (++stage == kStages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                        continue;
-                    }
-                    mbar_arrive_expect_tx(&bars->b_full[stage], (uint32_t)(4 * prm.kboxes * kBoxBytes));
-#pragma unroll
-                    for (int pl = 0; pl < 4; ++pl) {
-#pragma unroll
-                        for (int kb = 0; kb < 2; ++kb) {
-                            if (kb >= prm.kboxes) continue;
-                            unsigned char* dbox = dst + (pl * 2 + kb) * kBoxBytes;
-                            if (csize == 1) {
-                                tma_load_3d(&x_map, &bars->b_full[stage], dbox, kb * kBoxK, tt * kTileT, fslot * 4 + pl);
-                            } else if (((prm.kboxes > 1 ? pl * 2 + kb : pl) & 1) == (int)crank) {
-                                tma_load_3d_mc(&x_map, &bars->b_full[stage], dbox, kb * kBoxK, tt * kTileT, fslot * 4 + pl, cmask);
-                            }
-                        }
-                    }
-                    if (++stage == kStages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                    // optional L2 prefetch of the tile kPrefetch steps ahead.  Measured on the headline shape: 2 or 4
-                    // tiles ahead cost 3-5 % (the prefetch requests compete with the store stream), so it is off.
-                    if (kPrefetch > 0) {
-                        int ptt = tt + kPrefetch;
-                        long long pgrp = grp;
-                        while (ptt >= prm.t_tiles) {
-                            ptt -= prm.t_tiles;
-                            pgrp += n_clusters;
-                        }
-                        if (pgrp < prm.groups) {
-                            const int pf = (int)(pgrp / prm.lt_groups);
-#pragma unroll
-                            for (int pl = 0; pl < 4; ++pl) {
-#pragma unroll
-                                for (int kb = 0; kb < 2; ++kb) {
-                                    if (kb >= prm.kboxes) continue;
-                                    if (csize == 1 || ((prm.kboxes > 1 ? pl * 2 + kb : pl) & 1) == (int)crank)
-                                        tma_prefetch_3d(&x_map, kb * kBoxK, ptt * kTileT, (pf % prm.ring) * 4 + pl);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        const int t_tail = (int)(prm.T - (long long)(prm.t_tiles - 1) * kTileT);
-        const int t_tail16 = ((t_tail + 15) >> 4) << 4;
-        int stage = 0, acc = 0;
-        uint32_t phase = 0, acc_phase = 0, a_phase = 0;
-        for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
-            long long f;
-            int lt;
-            decode(grp, f, lt);
-            if (lt >= prm.ltiles) {
-                // ghost tile: consume the multicast stream, compute nothing
-                for (int tt = 0; tt < prm.t_tiles; ++tt) {
-                    mbar_wait(&bars->b_full[stage], phase);
-                    if (elect_one_sync()) tcgen05_commit_mc(&bars->b_empty[stage], cmask);
-                    __syncwarp();
-                    if (++stage == kStages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-                if (prm.conv_D > 0 && lane == 0) red_release_add(prm.done + f, 1);
-                continue;
-            }
-            mbar_wait(&bars->a_full, a_phase);
-            for (int tt = 0; tt < prm.t_tiles; ++tt) {
-                mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
-                mbar_wait(&bars->b_full[stage], phase);
-                tcgen05_fence_after();
-                const int n_mma = (tt == prm.t_tiles - 1) ? t_tail16 : kTileT;
-                const uint32_t idesc = make_idesc(kTileL, n_mma, false);
-                const uint32_t idesc_neg = make_idesc(kTileL, n_mma, true);
-                const uint32_t idesc_bf = make_idesc(kTileL, n_mma, false, true);
-                const uint32_t idesc_bf_neg = make_idesc(kTileL, n_mma, true, true);
-                if (elect_one_sync()) {
-                    const uint32_t sbase = smem_u32(stage_base + (size_t)stage * kStageBytes);
-                    const uint64_t bdesc = make_b_desc(sbase);
-                    const uint32_t d_re = tmem + acc * kAccCols;
-                    const uint32_t d_im = d_re + kTileT;
-                    const uint32_t a0 = tmem + kOperandCol0;
-                    constexpr int kPasses = kHybrid ? 2 : 3;
-#pragma unroll
-                    for (int pass = 0; pass < kPasses; ++pass) {
-                        // planes {re_hi, im_hi, re_x, im_x}; x = lo (fp32) or packed bf16 pairs.
-                        // 3xTF32: (A, B) = (hi, hi) (hi, lo) (lo, hi).  hybrid: tf32 (hi, hi), then bf16 (x, x).
-                        const int ap = kHybrid ? (pass == 1 ? 2 : 0) : ((pass == 2) ? 2 : 0);
-                        const int bp = kHybrid ? (pass == 1 ? 2 : 0) : ((pass == 1) ? 2 : 0);
-                        const bool bf = kHybrid && pass == 1;
-#pragma unroll
-                        for (int ks = 0; ks < kMaxK / 8; ++ks) {
-                            if (ks < prm.ksteps && !(prm.debug & 8)) {
-                                const int kb = ks >> 2, kk = ks & 3;
-                                const uint64_t b_re = bdesc + (uint64_t)((((bp + 0) * 2 + kb) * kBoxBytes + kk * 32) >> 4);
-                                const uint64_t b_im = bdesc + (uint64_t)((((bp + 1) * 2 + kb) * kBoxBytes + kk * 32) >> 4);
-                                const uint32_t a_re = a0 + (ap + 0) * kMaxK + ks * 8;
-                                const uint32_t a_im = a0 + (ap + 1) * kMaxK + ks * 8;
-                                const uint32_t accum = (pass == 0 && ks == 0) ? 0u : 1u;
-                                if (bf) {
-                                    umma_bf16_ts(d_re, a_re, b_re, idesc_bf, accum);
-                                    umma_bf16_ts(d_re, a_im, b_im, idesc_bf_neg, 1u);
-                                    umma_bf16_ts(d_im, a_re, b_im, idesc_bf, accum);
-                                    umma_bf16_ts(d_im, a_im, b_re, idesc_bf, 1u);
-                                } else {
-                                    umma_tf32_ts(d_re, a_re, b_re, idesc, accum);
-                                    umma_tf32_ts(d_re, a_im, b_im, idesc_neg, 1u);
-                                    umma_tf32_ts(d_im, a_re, b_im, idesc, accum);
-                                    umma_tf32_ts(d_im, a_im, b_re, idesc, 1u);
-                                }
-                            }
-                        }
-                    }
-                    if (csize == 1) tcgen05_commit(&bars->b_empty[stage]);
-                    else tcgen05_commit_mc(&bars->b_empty[stage], cmask);
-                    tcgen05_commit(&bars->acc_full[acc]);
-                    if (tt == prm.t_tiles - 1) {
-                        tcgen05_commit(&bars->a_empty);
-                        // every plane box of this task has landed in shared memory (b_full of the last tile was
-                        // waited for above): the slot of bin f may be overwritten once all nsl tasks have said so
-                        if (prm.conv_D > 0) red_release_add(prm.done + f, 1);
-                    }
-                }
-                __syncwarp();
-                if (++stage == kStages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_phase ^= 1;
-                }
-            }
-            a_phase ^= 1;
-        }
-    } else if (prm.conv_D > 0) {
-        // ===================== converters (warps 2, 3): split the spectra of a bin conv_D bins ahead =====================
-        convert_ahead<kHybrid>(prm, bars, conv_base, warp - 2, lane, cluster_id, n_clusters, (int)crank);
-    }
-    } else if (warp >= kBuildWarp0) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsBuild));
-        // ===================== builders: A_f tile = sum_g d_f[g] G_g  ->  registers -> TMEM =====================
-        // warp (quarter, half): rows quarter*32 + lane of the l-tile, mic columns [half*32, half*32 + 32)
-        const int quarter = warp & 3;
-        const int half = (warp - kBuildWarp0) >> 2;
-        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        const int row = quarter * 32 + lane;
-        // column pairs this warp owns that actually exist (Kh = ksteps * 4 pairs; pairs beyond it stay zero)
-        int npairs = prm.Kh - half * 16;
-        npairs = npairs < 0 ? 0 : (npairs > 16 ? 16 : npairs);
-        uint32_t a_phase = 0;
-#if SFA_FUSED_G2_HINT
-        const uint64_t g2_pol = l2_policy_evict_last();
-#endif
-        for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
-            long long f;
-            int lt;
-            decode(grp, f, lt);
-            if (lt >= prm.ltiles) continue;
-            float2 dg[NG];
-#pragma unroll
-            for (int g = 0; g < NG; ++g)
-                dg[g] = (g < prm.ngroups) ? __ldg(prm.d + f * prm.ngroups + g) : make_float2(0.f, 0.f);
-            float are[32], aim[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) are[j] = aim[j] = 0.f;
-            const float4* gp = prm.G2 + ((size_t)lt * prm.ngroups * prm.Kh + (size_t)half * 16) * kTileL + row;
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                if (g < prm.ngroups && !(prm.debug & 2)) {
-                    const float4* gg = gp + (size_t)g * prm.Kh * kTileL;
-                    // all 16 loads of the group are issued before the first FMA (memory-level parallelism)
-                    float4 v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-#if SFA_FUSED_G2_HINT
-                        v[j] = (j < npairs) ? ldg_hint(gg + (size_t)j * kTileL, g2_pol) : make_float4(0.f, 0.f, 0.f, 0.f);
-#else
-                        v[j] = (j < npairs) ? __ldg(gg + (size_t)j * kTileL) : make_float4(0.f, 0.f, 0.f, 0.f);
-#endif
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        are[2 * j] = fmaf(dg[g].x, v[j].x, are[2 * j]);
-                        are[2 * j] = fmaf(-dg[g].y, v[j].y, are[2 * j]);
-                        aim[2 * j] = fmaf(dg[g].x, v[j].y, aim[2 * j]);
-                        aim[2 * j] = fmaf(dg[g].y, v[j].x, aim[2 * j]);
-                        are[2 * j + 1] = fmaf(dg[g].x, v[j].z, are[2 * j + 1]);
-                        are[2 * j + 1] = fmaf(-dg[g].y, v[j].w, are[2 * j + 1]);
-                        aim[2 * j + 1] = fmaf(dg[g].x, v[j].w, aim[2 * j + 1]);
-                        aim[2 * j + 1] = fmaf(dg[g].y, v[j].z, aim[2 * j + 1]);
-                    }
-                }
-            }
-            // the MMAs of the previous task must have finished reading the operand columns
-            mbar_wait(&bars->a_empty, a_phase ^ 1);
-            tcgen05_fence_after();
-            const uint32_t col = tmem + lane_base + kOperandCol0 + half * 32;
-            uint32_t w[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) w[j] = to_tf32(are[j]);
-            SFA_TMEM_ST32(col + 0 * kMaxK, w);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float h = __uint_as_float(to_tf32(are[j]));
-                w[j] = kHybrid ? pack_bf16(h, are[j] - h) : __float_as_uint(are[j] - h);     // A side: (hi, lo)
-            }
-            SFA_TMEM_ST32(col + 2 * kMaxK, w);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) w[j] = to_tf32(aim[j]);
-            SFA_TMEM_ST32(col + 1 * kMaxK, w);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float h = __uint_as_float(to_tf32(aim[j]));
-                w[j] = kHybrid ? pack_bf16(h, aim[j] - h) : __float_as_uint(aim[j] - h);
-            }
-            SFA_TMEM_ST32(col + 3 * kMaxK, w);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->a_full);
-            a_phase ^= 1;
-        }
-    } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
-        // ===================== epilogue: TMEM -> regs -> swizzled smem boxes -> TMA store =====================
-        // warp owns TMEM lane quarter (warp & 3) = 32 look directions; per frame tile two passes of 32 frames.
-        const int quarter = warp & 3;
-        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        unsigned char* const my_store = store_base + (size_t)(warp - kEpiWarp0) * kStoreWarpBytes;
-        // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
-        const uint32_t row_off = (uint32_t)lane * 128u;
-        const uint32_t sw = (uint32_t)(lane & 7);
-        int acc = 0, buf = 0;
-        uint32_t acc_phase = 0;
-        const uint64_t st_pol = l2_policy_evict_first();
-        const bool st_hint = prm.store_evict_first != 0;
-        for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
-            long long f;
-            int lt;
-            decode(grp, f, lt);
-            if (lt >= prm.ltiles) continue;
-            const int l0 = lt * kTileL + quarter * 32;
-            float psum = 0.f;                                    // sum_t |q[f, l0 + lane, t]|^2
-            for (int tt = 0; tt < prm.t_tiles; ++tt) {
-                mbar_wait(&bars->acc_full[acc], acc_phase);
-                tcgen05_fence_after();
-#pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    const uint32_t t_re = tmem + lane_base + acc * kAccCols + pass * 32;
-                    uint32_t re[32], im[32];
-                    SFA_TMEM_LD32(t_re, re);
-                    SFA_TMEM_LD32(t_re + kTileT, im);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (pass == 1) {
-                        // the whole accumulator of this warp's lanes is in registers: release it
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
-                    }
-                    const long long t0 = (long long)tt * kTileT + pass * 32;
-                    if (t0 >= prm.T || l0 >= prm.L) continue;                   // warp-uniform
-                    if (prm.power) {
-                        const int nval = (prm.T - t0 >= 32) ? 32 : (int)(prm.T - t0);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (j < nval) {
-                                const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
-                                psum = fmaf(xr, xr, fmaf(xi, xi, psum));
-                            }
-                        }
-                    }
-                    unsigned char* const sbuf = my_store + (size_t)buf * 2 * kStoreBoxBytes;
-                    // the stores issued from this slot kStoreRing passes ago must have finished reading it
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStoreRing - 1) : "memory");
-                    __syncwarp();
-                    if (!(prm.debug & 4))
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-                        unsigned char* const box = sbuf + b * kStoreBoxBytes + row_off;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const int j = 16 * b + 2 * c;
-                            *reinterpret_cast<float4*>(box + (((uint32_t)c ^ sw) << 4)) =
-                                make_float4(__uint_as_float(re[j]), __uint_as_float(im[j]),
-                                            __uint_as_float(re[j + 1]), __uint_as_float(im[j + 1]));
-                        }
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0 && !(prm.debug & 1)) {
-                        if (st_hint) {
-                            tma_store_3d_hint(&o_map, sbuf, (int)(2 * t0), l0, (int)f, st_pol);
-                            if (t0 + 16 < prm.T)
-                                tma_store_3d_hint(&o_map, sbuf + kStoreBoxBytes, (int)(2 * (t0 + 16)), l0, (int)f, st_pol);
-                        } else {
-                            tma_store_3d(&o_map, sbuf, (int)(2 * t0), l0, (int)f, false);
-                            if (t0 + 16 < prm.T)
-                                tma_store_3d(&o_map, sbuf + kStoreBoxBytes, (int)(2 * (t0 + 16)), l0, (int)f, false);
-                        }
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    if (++buf == kStoreRing) buf = 0;
-                }
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_phase ^= 1;
-                }
-            }
-            if (prm.power && l0 + lane < prm.L) prm.power[f * prm.Lrows + l0 + lane] = psum / (float)prm.T;
-        }
-    }
-
-    // outstanding bulk stores of this thread (epilogue issuers) must complete before the CTA exits
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    tcgen05_fence_before();
-    __syncthreads();
-    if (csize > 1) cluster_sync_all();
-    if (warp == 1) {
-        tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
-    }
-}
-
-// Stream-ahead conversion (warps 2 and 3 of every CTA, 64 threads, <= 56 registers).
-// `convert_slice` turns slice j of bin f' -- the 32-frame tiles j, j + nsl, ... of X[f'] -- into the four K-major
-// planes the TMA producer streams (same arithmetic as x_split_tail_kernel): the tile comes in with 8-byte
-// cp.async copies (all 32 per thread in flight at once: no registers, one DRAM latency per tile), is read back
-// transposed and written along q.  The tail look directions of those frames are computed from the tile that
-// is in shared memory anyway.  Schedule:
-//   * prologue: the grid converts the first conv_D bins, unit (bin, slice) = blockIdx.x, + gridDim.x, ...;
-//   * main loop: the CTA-task (bin f, slice j) converts slice j of bin f + conv_D.  The planes live in a RING of
-//     `ring` bin slots (bin f in slot f mod ring, ~40 MB, L2-resident): a slot is overwritten while its lines are
-//     still dirty in L2, so the planes are never written back -- DRAM sees X once and the beams once -- and the
-//     pre-pass over all bins (0.38 ms of a 5.4 ms step) disappears.  The converters run ahead of their CTA as far
-//     as the ring allows: before writing slot s they wait until every task of the bin that held it has received
-//     its planes (done[f' - ring] == nsl, signalled by the MMA warps).
-// Hand-over: every thread fences its stores, the 64 threads meet on named barrier 1, one thread adds 1 to
-// ready[f'] (release); the TMA producer of a task on bin f' spins on ready[f'] == nsl (acquire) and issues a
-// proxy fence before its first load.  The converters never wait for anything but their own CTA reaching the
-// task, so the dependency chain runs strictly towards lower bins and ends at the prologue.
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-
-template <bool kHybrid>
-__device__ __forceinline__ void convert_slice(const Params& prm, unsigned char* smem, int cw, int lane, long long fc,
-                                              int slice) {
-    float2 (*tile)[kConvT + 1] = reinterpret_cast<float2 (*)[kConvT + 1]>(smem);
-    float2 (*sA)[kMaxK] = reinterpret_cast<float2 (*)[kMaxK]>(smem + kMaxK * (kConvT + 1) * 8);
-    float* spow = reinterpret_cast<float*>(smem + kMaxK * (kConvT + 1) * 8 + kTailMaxRows * kMaxK * 8);
-    const int tid = cw * 32 + lane;
-    const long long T = prm.T;
-    const int Q = prm.Q, Kp = prm.Kp, rem = prm.rem;
-    const int n32 = (int)((T + kConvT - 1) / kConvT);
-    const long long plane = T * Kp;
-    const float2* const xf = prm.X + fc * Q * T;
-    float* const base = prm.Xs + (fc % prm.ring) * 4 * plane;
-    const uint64_t keep = l2_policy_evict_last();
-    if (fc >= prm.ring) {
-        // the slot still holds bin fc - ring until every task of that bin has received its planes (two rounds of
-        // tasks ago in the normal course of events, so this does not spin)
-        if (tid == 0)
-            while (ld_acquire_gpu(prm.done + (fc - prm.ring)) < prm.nsl) __nanosleep(64);
-        named_bar_sync(1, 64);
-    }
-    if (rem > 0) {
-        for (int i = tid; i < rem * prm.Kh; i += 64) {
-            const int r = i / prm.Kh, j = i - r * prm.Kh;
-            float ar0 = 0.f, ai0 = 0.f, ar1 = 0.f, ai1 = 0.f;
-            for (int g = 0; g < prm.ngroups; ++g) {
-                const float2 dg = __ldg(prm.d + fc * prm.ngroups + g);
-                const float4 v = __ldg(prm.G2_last + ((size_t)g * prm.Kh + j) * kTileL + r);
-                ar0 = fmaf(dg.x, v.x, ar0);
-                ar0 = fmaf(-dg.y, v.y, ar0);
-                ai0 = fmaf(dg.x, v.y, ai0);
-                ai0 = fmaf(dg.y, v.x, ai0);
-                ar1 = fmaf(dg.x, v.z, ar1);
-                ar1 = fmaf(-dg.y, v.w, ar1);
-                ai1 = fmaf(dg.x, v.w, ai1);
-                ai1 = fmaf(dg.y, v.z, ai1);
-            }
-            sA[r][2 * j] = make_float2(ar0, ai0);
-            sA[r][2 * j + 1] = make_float2(ar1, ai1);
-        }
-        for (int r = cw + 2 * lane; r < rem; r += 64) spow[r] = 0.f;      // row r belongs to warp r & 1
-        __syncwarp();
-    }
-    for (int tile_no = slice; tile_no < n32; tile_no += prm.nsl) {
-        const long long t0 = (long long)tile_no * kConvT;
-        named_bar_sync(1, 64);                                 // previous tile consumed, sA complete
-        // load: warp cw takes the microphones [32 cw, 32 cw + 32), lane = frame (coalesced along t)
-        {
-            const long long t = t0 + lane;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int q = cw * 32 + i;
-                if (q < Q && t < T && !(prm.debug & 32)) cp_async8(&tile[q][lane], xf + (long long)q * T + t);
-                else tile[q][lane] = make_float2(0.f, 0.f);
-            }
-            asm volatile("cp.async.wait_all;" ::: "memory");
-        }
-        named_bar_sync(1, 64);
-        // planes: lane = microphone within the half, loop over the frames of the tile (writes along q)
-        {
-            const int q = cw * 32 + lane;
-            if (q < Kp && !(prm.debug & 64)) {
-#pragma unroll 4
-                for (int i = 0; i < kConvT; ++i) {
-                    const long long t = t0 + i;
-                    if (t < T) {
-                        const float2 v = tile[q][i];
-                        const float hr = __uint_as_float(to_tf32(v.x)), hi = __uint_as_float(to_tf32(v.y));
-                        float xr = v.x - hr, xi = v.y - hi;
-                        if (kHybrid) {                          // B side: (lo, hi) = (even, odd) bf16 k
-                            xr = __uint_as_float(pack_bf16(xr, hr));
-                            xi = __uint_as_float(pack_bf16(xi, hi));
-                        }
-                        float* o = base + t * Kp + q;
-                        st_f32_hint(o, hr, keep);
-                        st_f32_hint(o + plane, hi, keep);
-                        st_f32_hint(o + 2 * plane, xr, keep);
-                        st_f32_hint(o + 3 * plane, xi, keep);
-                    }
-                }
-            }
-        }
-        // tail look directions: warp cw takes the rows cw, cw + 2, ...; lane = frame
-        for (int r = cw; r < rem; r += 2) {
-            const long long t = t0 + lane;
-            float ar = 0.f, ai = 0.f;
-            for (int q = 0; q < Q; ++q) {
-                const float2 a = sA[r][q];
-                const float2 x = tile[q][lane];
-                ar = fmaf(a.x, x.x, ar);
-                ar = fmaf(-a.y, x.y, ar);
-                ai = fmaf(a.x, x.y, ai);
-                ai = fmaf(a.y, x.x, ai);
-            }
-            float p = 0.f;
-            if (t < T) {
-                prm.out[(fc * prm.Lrows + prm.Lm + r) * prm.ldo + t] = make_float2(ar, ai);
-                p = ar * ar + ai * ai;
-            }
-            if (prm.power) {
-                for (int off = 16; off; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
-                if (lane == 0) spow[r] += p;
-            }
-        }
-    }
-    if (prm.power && rem > 0) {
-        __syncwarp();
-        for (int r = cw + 2 * lane; r < rem; r += 64)
-            prm.tail_part[((size_t)fc * prm.nsl + slice) * kTailMaxRows + r] = spow[r];
-    }
-    __threadfence();
-    asm volatile("fence.proxy.async;" ::: "memory");
-    named_bar_sync(1, 64);
-    if (tid == 0) {
-        const int old = atomicAdd(prm.ready + fc, 1);
-        if (old == prm.nsl - 1 && prm.power && rem > 0) {
-            // last slice of the bin: sum the partial power sums of the tail rows in a fixed order
-            __threadfence();
-            for (int r = 0; r < rem; ++r) {
-                float acc = 0.f;
-                for (int sl = 0; sl < prm.nsl; ++sl)
-                    acc += __ldcg(prm.tail_part + ((size_t)fc * prm.nsl + sl) * kTailMaxRows + r);
-                prm.power[fc * prm.Lrows + prm.Lm + r] = acc / (float)T;
-            }
-        }
-    }
-}
-
-// L2 prefetch of the X rows of one slice (64 threads: one 256-byte row piece per thread and tile)
-__device__ __forceinline__ void prefetch_slice(const Params& prm, int tid, long long fc, int slice) {
-    const long long T = prm.T;
-    const int n32 = (int)((T + kConvT - 1) / kConvT);
-    if (tid >= prm.Q) return;
-    const float2* row = prm.X + (fc * prm.Q + tid) * T;
-    for (int tile_no = slice; tile_no < n32; tile_no += prm.nsl) {
-        const long long t0 = (long long)tile_no * kConvT;
-        // whole 128-byte lines covering [t0, t0 + 32) of the row (rows are only 8-byte aligned)
-        const uintptr_t a0 = reinterpret_cast<uintptr_t>(row + t0) & ~(uintptr_t)127;
-        const long long tend = t0 + kConvT < T ? t0 + kConvT : T;
-        const uintptr_t a1 = reinterpret_cast<uintptr_t>(row + tend);
-        for (uintptr_t a = a0; a < a1; a += 128)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a) : "memory");
-    }
-}
-
-template <bool kHybrid>
-__device__ void convert_ahead(const Params& prm, Barriers* bars, unsigned char* smem, int cw, int lane,
                               long long cluster_id, long long n_clusters, int crank) {
     (void)bars;
     // prologue: the first conv_D bins, spread over the whole grid
