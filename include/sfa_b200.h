@@ -68,8 +68,9 @@ int sfa_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* Library-wide tuning knobs (process-global, initialised once at load time from the SFA_<KEY> environment
  * variables; no launch path calls getenv).  Keys: "pwd_chunk_mb" (scratch budget per frequency slab),
- * "no_fused", "fused_prepass", "no_kloop", "no_cluster", "no_fold", "no_tma_store", "old_build" (0/1: switch a kernel
- * variant off -- test and tuning use), "kloop_block", "issuers", "fused_D", "fused_ring" (0 = automatic).  Unknown key: SFA_ERR_INVALID / NaN. */
+ * "no_fused", "fused_prepass", "fft_generic", "no_kloop", "no_cluster", "no_fold", "no_tma_store", "old_build" (0/1: switch a kernel
+ * variant off -- test and tuning use), "kloop_block", "issuers", "fused_D", "fused_ring" (0 = automatic),
+ * "reserve_sms" (SMs the persistent kernels leave free, e.g. for NCCL copy kernels running under them).  Unknown key: SFA_ERR_INVALID / NaN. */
 int sfa_set_option(const char* key, double value);
 double sfa_get_option(const char* key);
 
@@ -227,6 +228,13 @@ int sfa_pwd_host_destroy(sfa_pwd_host_ctx* ctx);
 /* pinned host memory helpers for the host path */
 int sfa_host_alloc(void** p, size_t bytes);
 int sfa_host_free(void* p);
+
+/* Multi-GPU exchange of the beam tensor ("only an all-gather of the output beam maps"): DMA copy of
+ * `bytes` from `src` (device src_dev) into `dst` (device dst_dev; typically a peer rank's output buffer mapped
+ * over CUDA IPC), asynchronous on `stream` (a stream of src_dev).  Runs on the copy engines over
+ * NVLink / NVSwitch, so it overlaps the persistent tensor-core kernels that own every SM.  Enables peer access on
+ * first use; SFA_ERR_UNSUPPORTED when the two devices have no peer path. */
+int sfa_peer_copy(void* dst, int dst_dev, const void* src, int src_dev, size_t bytes, void* stream);
 
 /* Beam power map mean_t |q[f,l,t]|^2 (what the reference's examples plot as db(q), e.g.
  * doc/examples/modal_beamforming_rigid_spherical_array.py:43-57, and the all-gathered quantity of the

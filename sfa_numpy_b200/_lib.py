@@ -49,6 +49,7 @@ SIGNATURES = {
     "sfa_legendre_matrix": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "sfa_grid_points": (c_int64, [c_int, c_int]),
     "sfa_grid": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sfa_peer_copy": (c_int, [c_void_p, c_int, c_void_p, c_int, c_size_t, c_void_p]),
     "sfa_matdiagmul": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sfa_norm_of_columns": (c_int, [c_int64, c_int64, c_void_p, c_double, c_void_p, c_void_p]),
     "sfa_coherence_of_columns": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -461,16 +461,22 @@ cgemm3x_kloop_kernel(const __grid_constant__ CUtensorMap p_map, const Params prm
 
 // Accumulation block (in 32-k chunks): keeps the truncation bias of the tensor-core accumulate at
 // ~6e-6 of the result through both GEMMs of the factored form (measured 2.1e-8 / 3.2e-8 per k).
-static int kloop_block_chunks(int hybrid) {
+// At most 10 (hybrid) / 7 (3xTF32) chunks per block, the chunks spread evenly over the blocks: K = 289
+// (cfg 4, second product) is ONE block of 10 -- accumulators straight to the output, no scratch round trip:
+// 1.98 -> 1.64 ms for cfg 4 -- and K = 1089 (cfg 5) stays at 4 blocks of 9 (error 5.9e-6; 3 blocks of 12
+// would be 1 % faster at 7.6e-6).  tools/kloop_block_probe.py.
+static int kloop_block_chunks(long long kchunks, int hybrid) {
     if (options().kloop_block > 0) return options().kloop_block;
-    return hybrid ? 9 : 6;
+    const long long cap = hybrid ? 10 : 7;
+    const long long nblocks = ceil_div(kchunks, cap);
+    return (int)ceil_div(kchunks, nblocks < 1 ? 1 : nblocks);
 }
 
 // Scratch the launch needs for a product with inner dimension K (0 when one block covers K).
 size_t cgemm3x_kloop_scratch_bytes(long long K, int hybrid) {
     using namespace kloop;
     const long long kchunks = ceil_div(K, kChunkK);
-    const long long nblocks = ceil_div(kchunks, kloop_block_chunks(hybrid));
+    const long long nblocks = ceil_div(kchunks, kloop_block_chunks(kchunks, hybrid));
     if (nblocks <= 1) return 0;
     return (size_t)sm_count() * kTileN * kTileM * sizeof(float2);
 }
@@ -519,7 +525,7 @@ int launch_cgemm3x_kloop(long long B, long long Nn, long long Mm, long long K, c
     prm.n_tiles = (int)ceil_div(Nn, kTileN);
     prm.tasks = (long long)prm.n_tiles * prm.m_groups;
     prm.kchunks = (int)ceil_div(K, kChunkK);
-    prm.block_chunks = kloop_block_chunks(hybrid);
+    prm.block_chunks = kloop_block_chunks(prm.kchunks, hybrid);
     prm.nblocks = (int)ceil_div(prm.kchunks, prm.block_chunks);
     prm.scratch = reinterpret_cast<float2*>(scratch);
     if (prm.nblocks > 1 && (!scratch || scratch_bytes < cgemm3x_kloop_scratch_bytes(K, hybrid) || ((uintptr_t)scratch & 7)))
@@ -527,7 +533,7 @@ int launch_cgemm3x_kloop(long long B, long long Nn, long long Mm, long long K, c
     const size_t smem = (size_t)kStages * kStageBytes + 2 * kPieceBytes + sizeof(Barriers) + 1024;
     if (hybrid) SFA_ENSURE_DYN_SMEM(cgemm3x_kloop_kernel<true>, smem);
     else SFA_ENSURE_DYN_SMEM(cgemm3x_kloop_kernel<false>, smem);
-    const long long max_clusters = sm_count() / csize;
+    const long long max_clusters = persistent_sms() / csize;
     const long long grid = (prm.tasks < max_clusters ? prm.tasks : max_clusters) * csize;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);

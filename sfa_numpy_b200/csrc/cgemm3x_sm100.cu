@@ -583,7 +583,7 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     prm.csize = csize;
     prm.m_groups = (prm.m_tiles + csize - 1) / csize;
     const long long n_groups = (fold ? 1 : B) * prm.m_groups;
-    const long long max_clusters = sm_count() / csize;
+    const long long max_clusters = persistent_sms() / csize;
     const long long grid = (n_groups < max_clusters ? n_groups : max_clusters) * csize;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);

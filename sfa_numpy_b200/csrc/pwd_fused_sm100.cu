@@ -970,7 +970,7 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     prm.groups = nf * prm.lt_groups;
     prm.power = power;
     prm.store_evict_first = ((double)nf * (double)L * (double)ldo * 8.0 > 256e6) ? 1 : 0;     // >> L2 (126 MB)
-    const long long max_clusters = sm_count() / prm.csize;
+    const long long max_clusters = persistent_sms() / prm.csize;
     const long long n_clusters = prm.groups < max_clusters ? prm.groups : max_clusters;
     // Stream-ahead conversion: the CTAs working on bin f split the spectra of bin f + D, D = the number of bins
     // the grid works on at once, plus two of slack; the first D bins come from the pre-pass.  Only worth it when

@@ -70,9 +70,17 @@ struct Options {
     int old_build;         // steering build: generic kernel instead of the few-groups fast kernel
     int no_fused;          // steering form: slab build + GEMM launches instead of the fused persistent kernel
     int fused_prepass;     // fused kernel: split ALL spectra in the pre-pass kernel (no in-kernel stream-ahead conversion)
+    int fft_generic;       // irfft / stft: the generic radix-4 ping-pong kernel instead of the radix-16 fast path
+    int reserve_sms;       // SMs the persistent tensor-core kernels leave free (for NCCL's copy kernels when a collective
+                           // is meant to run under them)
     int fused_D, fused_ring; // stream-ahead distance / plane-ring size of the fused kernel in bins (0 = automatic)
     int fused_debug;       // timing-attribution switches of the fused kernel; honoured by SFA_DEBUG_HOOKS builds only
 };
 Options& options();
+// SMs a persistent kernel may occupy: all of them minus options().reserve_sms (at least 2)
+static inline int persistent_sms() {
+    int n = sm_count() - options().reserve_sms;
+    return n < 2 ? 2 : n;
+}
 
 }  // namespace sfa

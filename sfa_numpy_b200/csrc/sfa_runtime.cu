@@ -43,6 +43,8 @@ static Options make_options() {
     o.old_build = env_flag("SFA_OLD_BUILD");
     o.no_fused = env_flag("SFA_NO_FUSED");
     o.fused_prepass = env_flag("SFA_FUSED_PREPASS");
+    o.fft_generic = env_flag("SFA_FFT_GENERIC");
+    o.reserve_sms = (int)env_num("SFA_RESERVE_SMS", 0.0);
     o.fused_D = (int)env_num("SFA_FUSED_D", 0.0);
     o.fused_ring = (int)env_num("SFA_FUSED_RING", 0.0);
     o.fused_debug = (int)env_num("SFA_FUSED_DEBUG", 0.0);
@@ -191,6 +193,8 @@ static double* option_slot(const char* key, int** islot) {
     else if (!strcmp(key, "old_build")) *islot = &o.old_build;
     else if (!strcmp(key, "no_fused")) *islot = &o.no_fused;
     else if (!strcmp(key, "fused_prepass")) *islot = &o.fused_prepass;
+    else if (!strcmp(key, "fft_generic")) *islot = &o.fft_generic;
+    else if (!strcmp(key, "reserve_sms")) *islot = &o.reserve_sms;
     else if (!strcmp(key, "fused_D")) *islot = &o.fused_D;
     else if (!strcmp(key, "fused_ring")) *islot = &o.fused_ring;
     else if (!strcmp(key, "fused_debug")) *islot = &o.fused_debug;
@@ -249,6 +253,36 @@ int sfa_host_alloc(void** p, size_t bytes) {
 
 int sfa_host_free(void* p) {
     if (p) SFA_CUDA_CHECK(cudaFreeHost(p));
+    return SFA_OK;
+}
+
+// Peer-to-peer DMA copy (copy engines over NVLink / NVSwitch; no SM involved): `bytes` from `src` on device
+// `src_dev` to `dst` on device `dst_dev` -- `dst` may be another process's buffer mapped over CUDA IPC --
+// asynchronously on `stream` (a stream of src_dev).  Peer access is enabled in both directions on first use.
+int sfa_peer_copy(void* dst, int dst_dev, const void* src, int src_dev, size_t bytes, void* stream) {
+    if (bytes == 0) return SFA_OK;
+    if (!dst || !src || dst_dev < 0 || src_dev < 0 || dst_dev >= 64 || src_dev >= 64) return SFA_ERR_INVALID;
+    static unsigned char enabled[64][64];
+    if (dst_dev != src_dev && !enabled[src_dev][dst_dev]) {
+        int can = 0, cur = -1;
+        SFA_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, src_dev, dst_dev));
+        if (!can) return SFA_ERR_UNSUPPORTED;
+        SFA_CUDA_CHECK(cudaGetDevice(&cur));
+        const int pairs[2][2] = {{src_dev, dst_dev}, {dst_dev, src_dev}};
+        for (int i = 0; i < 2; ++i) {
+            SFA_CUDA_CHECK(cudaSetDevice(pairs[i][0]));
+            cudaError_t e = cudaDeviceEnablePeerAccess(pairs[i][1], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+            else if (e != cudaSuccess) {
+                (void)cudaSetDevice(cur);
+                ::sfa::set_last_cuda_error(e, "cudaDeviceEnablePeerAccess");
+                return SFA_ERR_CUDA;
+            }
+        }
+        SFA_CUDA_CHECK(cudaSetDevice(cur));
+        enabled[src_dev][dst_dev] = 1;
+    }
+    SFA_CUDA_CHECK(cudaMemcpyPeerAsync(dst, dst_dev, src, src_dev, bytes, (cudaStream_t)stream));
     return SFA_OK;
 }
 }

@@ -280,6 +280,274 @@ stft_kernel(const StftParams prm, const R* __restrict__ x, const R* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Fast path (float, power-of-two length 256 .. 4096): radix-16 passes with the butterflies in REGISTERS.
+//   * the sequences of a tile live in ONE shared-memory buffer (no ping-pong): a pass reads the 16 (or 2/4/8)
+//     inputs of a butterfly into registers, the CTA synchronises, and the results go back in Stockham order --
+//     2048 points are 16 x 16 x 8: three passes instead of the six radix-4/2 passes of the generic kernel, a third
+//     of the barriers and of the shared-memory traffic;
+//   * index i of a sequence sits at i + i / 16, and the sequences are 2 elements further apart than that:
+//     the stride-16 writes of the first pass, the strided reads of the later ones and the pair-interleaved loads
+//     and stores of the global <-> shared phases are all free of bank conflicts;
+//   * half the footprint per column lets a tile hold 8 column pairs: every frequency row of the tile is one
+//     128-byte line of q (64 bytes of the real output).
+// ------------------------------------------------------------------------------------------------------------
+namespace fast {
+
+constexpr int kT = 512;
+__host__ __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
+__host__ __device__ __forceinline__ int seq_stride(int m) { return m + (m >> 4) + 2; }
+
+typedef cx<float> cf;
+
+// cos / sin of pi t / 8 for t = 1 .. 7 (compile-time t after unrolling: these fold to immediates)
+__device__ __forceinline__ constexpr float cos_pi8(int t) {
+    return t == 1 ? 0.92387953251128674f : t == 2 ? 0.70710678118654752f : t == 3 ? 0.38268343236508977f
+         : t == 5 ? -0.38268343236508977f : t == 6 ? -0.70710678118654752f : t == 7 ? -0.92387953251128674f : 0.f;
+}
+__device__ __forceinline__ constexpr float sin_pi8(int t) {
+    return t == 1 ? 0.38268343236508977f : t == 2 ? 0.70710678118654752f : t == 3 ? 0.92387953251128674f
+         : t == 5 ? 0.92387953251128674f : t == 6 ? 0.70710678118654752f : t == 7 ? 0.38268343236508977f : 1.f;
+}
+
+template <int R>
+__device__ __forceinline__ int brev(int i) {
+    int r = 0;
+#pragma unroll
+    for (int b = 1; b < R; b <<= 1) {
+        r = (r << 1) | (i & 1);
+        i >>= 1;
+    }
+    return r;
+}
+
+// In-register DFT of R points (decimation in frequency): afterwards v[i] holds output brev(i).
+// kInv: e^{+2 pi i jk/R}.  All loops unroll; the twiddles are compile-time constants.
+template <int R, bool kInv>
+__device__ __forceinline__ void dft_reg(cf (&v)[R]) {
+#pragma unroll
+    for (int half = R / 2; half >= 1; half >>= 1) {
+#pragma unroll
+        for (int base = 0; base < R; base += 2 * half) {
+#pragma unroll
+            for (int jj = 0; jj < half; ++jj) {
+                const cf a = v[base + jj], b = v[base + jj + half];
+                v[base + jj] = cadd(a, b);
+                const cf d = csub(a, b);
+                const int t = jj * (8 / half);                  // angle = pi t / 8
+                if (t == 0) {
+                    v[base + jj + half] = d;
+                } else if (t == 4) {                            // -i (forward) / +i (inverse)
+                    v[base + jj + half] = kInv ? mk<float>(-d.y, d.x) : mk<float>(d.y, -d.x);
+                } else {
+                    const float c = cos_pi8(t), sn = kInv ? sin_pi8(t) : -sin_pi8(t);
+                    v[base + jj + half] = mk<float>(d.x * c - d.y * sn, d.x * sn + d.y * c);
+                }
+            }
+        }
+    }
+}
+
+// One Stockham pass of radix R over `nseq` sequences of length m (in place, see above).  Ns = product of the
+// radices of the earlier passes.  blockDim.x = kT, m / R <= kT.  Ends with a barrier.
+template <int R, bool kInv>
+__device__ __forceinline__ void pass(cf* data, int sstride, const cf* __restrict__ tw, int m, int Ns, int nseq) {
+    const int per_seq = m / R;
+    const int G = kT / per_seq;                                 // sequences per round
+    const int s_in = threadIdx.x / per_seq, j = threadIdx.x - s_in * per_seq;
+    const int k = j & (Ns - 1);
+    const int tstep = m / (Ns * R);
+    const int j0 = (j - k) * R + k;
+    for (int s0 = 0; s0 < nseq; s0 += G) {
+        const int s = s0 + s_in;
+        const bool act = s < nseq;
+        cf v[R];
+        cf* a = data + (size_t)s * sstride;
+        if (act) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] = a[pad_idx(j + r * per_seq)];
+            if (k) {
+                // twiddles w^(r k tstep), r = 1 .. R-1: the powers of two come from the table (their addresses
+                // r k tstep are far apart -- up to 16-way bank conflicts if all R-1 were loaded), the others
+                // are products of at most three of them (error ~2e-7, well below the FP32 transform's own)
+                cf wp[R];
+#pragma unroll
+                for (int r = 1; r < R; r <<= 1) {
+                    wp[r] = tw[r * k * tstep];
+                    if (kInv) wp[r].y = -wp[r].y;
+                }
+#pragma unroll
+                for (int r = 3; r < R; ++r) {
+                    if (r & (r - 1)) {                          // not a power of two: top bit times the rest
+                        int top = 1;
+                        while (top * 2 <= r) top *= 2;
+                        wp[r] = cmul(wp[top], wp[r - top]);
+                    }
+                }
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[r] = cmul(v[r], wp[r]);
+            }
+            dft_reg<R, kInv>(v);
+        }
+        __syncthreads();                                        // every butterfly of the round has its inputs
+        if (act) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) a[pad_idx(j0 + brev<R>(r) * Ns)] = v[r];
+        }
+    }
+    __syncthreads();
+}
+
+// all passes for length m = 2^log2m (8 <= log2m <= 12): 16 x 16 x {1, 2, 4, 8, 16}
+template <bool kInv>
+__device__ __forceinline__ void fft_inplace(cf* data, int sstride, const cf* tw, int m, int log2m, int nseq) {
+    pass<16, kInv>(data, sstride, tw, m, 1, nseq);
+    pass<16, kInv>(data, sstride, tw, m, 16, nseq);
+    switch (log2m) {
+        case 9: pass<2, kInv>(data, sstride, tw, m, 256, nseq); break;
+        case 10: pass<4, kInv>(data, sstride, tw, m, 256, nseq); break;
+        case 11: pass<8, kInv>(data, sstride, tw, m, 256, nseq); break;
+        case 12: pass<16, kInv>(data, sstride, tw, m, 256, nseq); break;
+        default: break;
+    }
+}
+
+__global__ void __launch_bounds__(kT, 1)
+irfft_fast_kernel(const IrfftParams prm, const cf* __restrict__ q, float* __restrict__ out, const cf* __restrict__ tw_g) {
+    extern __shared__ unsigned char smem_raw[];
+    const int m = prm.m, nseq = prm.nseq;                        // nseq is a power of two
+    const int lg = 31 - __clz(nseq);
+    const int n = (int)prm.n;                                   // == m
+    const int sstride = seq_stride(m);
+    cf* tw = reinterpret_cast<cf*>(smem_raw);
+    cf* data = tw + m;
+    for (int i = threadIdx.x; i < m; i += kT) tw[i] = tw_g[i];
+    const int cols = 2 * nseq;
+    const long long tiles = (prm.C + cols - 1) / cols;
+    const int kmax = n / 2;
+    const float scale = (float)(1.0 / (double)n);
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long c0 = tile * cols;
+        __syncthreads();                                        // previous tile's stores have read `data`; tw is loaded
+        // load + Hermitian pack (every index 0 .. n-1 of every sequence is written: no zero fill needed).
+        // Eight independent 16-byte loads per thread are in flight before the first one is used: with one load
+        // per loop iteration this phase was a chain of ~16 DRAM latencies per tile.
+        const int items = (kmax + 1) * nseq;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(q) & 15) == 0) && ((prm.ld & 1) == 0);
+        for (int w0 = threadIdx.x; w0 < items; w0 += kT * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int w = w0 + u * kT;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (w < items) {
+                    const int k = w >> lg, s = w & (nseq - 1);
+                    const long long ca = c0 + 2 * s;
+                    if (k < prm.F && ca < prm.C) {
+                        const cf* row = q + (long long)k * prm.ld + ca;
+                        if (vec_ok && ca + 1 < prm.C) {
+                            v[u] = __ldg(reinterpret_cast<const float4*>(row));
+                        } else {
+                            const float2 a = __ldg(reinterpret_cast<const float2*>(row));
+                            v[u].x = a.x;
+                            v[u].y = a.y;
+                            if (ca + 1 < prm.C) {
+                                const float2 b = __ldg(reinterpret_cast<const float2*>(row + 1));
+                                v[u].z = b.x;
+                                v[u].w = b.y;
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int w = w0 + u * kT;
+                if (w < items) {
+                    const int k = w >> lg, s = w & (nseq - 1);
+                    cf xa = mk<float>(v[u].x, v[u].y), xb = mk<float>(v[u].z, v[u].w);
+                    const bool self_conj = (k == 0) || (2 * k == n);
+                    if (self_conj) {
+                        xa.y = 0.f;
+                        xb.y = 0.f;
+                    }
+                    cf* seq = data + (size_t)s * sstride;
+                    seq[pad_idx(k)] = mk<float>(xa.x - xb.y, xa.y + xb.x);                       // Xa + i Xb
+                    if (!self_conj) seq[pad_idx(n - k)] = mk<float>(xa.x + xb.y, xb.x - xa.y);   // conj(Xa) + i conj(Xb)
+                }
+            }
+        }
+        __syncthreads();
+        fft_inplace<true>(data, sstride, tw, m, prm.log2m, nseq);
+        // unpack: x_a[j] = Re z[j] / n, x_b[j] = Im z[j] / n
+#pragma unroll 4
+        for (int w = threadIdx.x; w < n * nseq; w += kT) {
+            const int j = w >> lg, s = w & (nseq - 1);
+            const cf z = data[(size_t)s * sstride + pad_idx(j)];
+            int jo = j + prm.shift;
+            if (jo >= n) jo -= n;
+            const long long ca = c0 + 2 * s;
+            float* o = out + (long long)jo * prm.ldo + ca;
+            if (ca + 1 < prm.C && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
+                *reinterpret_cast<float2*>(o) = make_float2(z.x * scale, z.y * scale);
+            } else {
+                if (ca < prm.C) o[0] = z.x * scale;
+                if (ca + 1 < prm.C) o[1] = z.y * scale;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kT, 1)
+stft_fast_kernel(const StftParams prm, const float* __restrict__ x, const float* __restrict__ win, cf* __restrict__ X,
+                 const cf* __restrict__ tw_g) {
+    extern __shared__ unsigned char smem_raw[];
+    const int n = prm.nfft, nseq = prm.nseq;                     // both powers of two
+    const int lg = 31 - __clz(nseq);
+    const int sstride = seq_stride(n);
+    cf* tw = reinterpret_cast<cf*>(smem_raw);
+    cf* data = tw + n;
+    for (int i = threadIdx.x; i < n; i += kT) tw[i] = tw_g[i];
+    const int frames = 2 * nseq;
+    const long long ttiles = (prm.T + frames - 1) / frames;
+    const long long tiles = prm.Q * ttiles;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long qi = tile / ttiles;
+        const long long t0 = (tile - qi * ttiles) * frames;
+        __syncthreads();
+        const float* xq = x + qi * prm.S;
+#pragma unroll 8
+        for (int w = threadIdx.x; w < nseq * n; w += kT) {
+            const int s = w >> prm.log2n, j = w & (n - 1);      // j fastest: coalesced along the signal
+            const long long ta = t0 + 2 * s, tb = ta + 1;
+            const float wj = win ? __ldg(win + j) : 1.f;
+            const float va = (ta < prm.T) ? __ldg(xq + ta * prm.hop + j) * wj : 0.f;
+            const float vb = (tb < prm.T) ? __ldg(xq + tb * prm.hop + j) * wj : 0.f;
+            data[(size_t)s * sstride + pad_idx(j)] = mk<float>(va, vb);
+        }
+        __syncthreads();
+        fft_inplace<false>(data, sstride, tw, n, prm.log2n, nseq);
+        // Xa[k] = (Z[k] + conj(Z[n-k])) / 2,  Xb[k] = (Z[k] - conj(Z[n-k])) / (2i); s fastest: 16 bytes per pair
+        for (long long w = threadIdx.x; w < prm.Fk * nseq; w += kT) {
+            const int k = (int)(w >> lg), s = (int)(w & (nseq - 1));
+            const cf* z = data + (size_t)s * sstride;
+            const cf zk = z[pad_idx(k)], zn = z[pad_idx((n - k) & (n - 1))];
+            const cf xa = mk<float>(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+            const cf xb = mk<float>(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+            const long long ta = t0 + 2 * s;
+            cf* o = X + ((long long)k * prm.Q + qi) * prm.T + ta;
+            if (ta < prm.T) o[0] = xa;
+            if (ta + 1 < prm.T) o[1] = xb;
+        }
+    }
+}
+
+static inline bool supported(long long m) { return m >= 256 && m <= 4096 && (m & (m - 1)) == 0; }
+static inline int pairs_per_tile(long long m) { return m <= 2048 ? 8 : 4; }
+static inline size_t smem_bytes(long long m, int nseq) { return ((size_t)m + (size_t)nseq * seq_stride((int)m)) * sizeof(cf); }
+
+}  // namespace fast
+
 static int ilog2(long long v) {
     int l = 0;
     while ((1LL << l) < v) ++l;
@@ -306,6 +574,31 @@ static int run_irfft(long long F, long long C, long long n, const void* q, long 
         SFA_ENSURE_DYN_SMEM(bluestein_setup_kernel<R>, smem);
         bluestein_setup_kernel<R><<<1, kThreads, smem, st>>>((int)n, (int)m, log2m, +1, tw, chirp, Bf);
         SFA_LAUNCH_CHECK();
+    }
+    if (sizeof(R) == 4 && pow2 && fast::supported(m) && !options().fft_generic) {
+        long long nseq = fast::pairs_per_tile(m);
+        while (nseq > 1 && nseq > (C + 1) / 2) nseq >>= 1;      // a power of two (index math by shifts)
+        IrfftParams prm;
+        prm.F = F;
+        prm.C = C;
+        prm.n = n;
+        prm.ld = ld;
+        prm.ldo = ldo;
+        prm.m = (int)m;
+        prm.log2m = log2m;
+        prm.nseq = (int)nseq;
+        prm.shift = shift ? (int)(n / 2) : 0;
+        const size_t smem = fast::smem_bytes(m, (int)nseq);
+        SFA_ENSURE_DYN_SMEM(fast::irfft_fast_kernel, smem);
+        long long blocks = ceil_div(C, 2 * nseq);
+        if (blocks > sm_count()) blocks = sm_count();
+        prof_begin(st);
+        fast::irfft_fast_kernel<<<(unsigned)blocks, fast::kT, smem, st>>>(prm, reinterpret_cast<const fast::cf*>(q),
+                                                                          reinterpret_cast<float*>(out),
+                                                                          reinterpret_cast<const fast::cf*>(tw));
+        prof_end(st);
+        SFA_LAUNCH_CHECK();
+        return SFA_OK;
     }
     // column pairs per tile: as many as fit in ~200 KB next to the twiddle table (capped at 8 = 16 columns)
     const size_t budget = 200 * 1024;
@@ -348,6 +641,29 @@ static int run_stft(long long Q, long long S, int nfft, int hop, long long Fk, c
     cx<R>* tw = reinterpret_cast<cx<R>*>(work);
     twiddle_kernel<R><<<(unsigned)ceil_div(nfft, 256), 256, 0, st>>>(nfft, tw);
     SFA_LAUNCH_CHECK();
+    if (sizeof(R) == 4 && fast::supported(nfft) && !options().fft_generic) {
+        long long nseq = fast::pairs_per_tile(nfft);
+        while (nseq > 1 && nseq > (T + 1) / 2) nseq >>= 1;
+        StftParams prm;
+        prm.Q = Q;
+        prm.S = S;
+        prm.T = T;
+        prm.nfft = nfft;
+        prm.hop = hop;
+        prm.log2n = ilog2(nfft);
+        prm.Fk = Fk;
+        prm.nseq = (int)nseq;
+        const size_t smem = fast::smem_bytes(nfft, (int)nseq);
+        SFA_ENSURE_DYN_SMEM(fast::stft_fast_kernel, smem);
+        long long blocks = Q * ceil_div(T, 2 * nseq);
+        if (blocks > sm_count()) blocks = sm_count();
+        fast::stft_fast_kernel<<<(unsigned)blocks, fast::kT, smem, st>>>(prm, reinterpret_cast<const float*>(x),
+                                                                         reinterpret_cast<const float*>(win),
+                                                                         reinterpret_cast<fast::cf*>(X),
+                                                                         reinterpret_cast<const fast::cf*>(tw));
+        SFA_LAUNCH_CHECK();
+        return SFA_OK;
+    }
     const size_t budget = 200 * 1024;
     long long nseq = ((long long)budget - (long long)(nfft * esz)) / (long long)(2 * nfft * esz);
     if (nseq < 1) return SFA_ERR_UNSUPPORTED;

@@ -6,8 +6,12 @@ why stage 2 is simply replicated: it is a few MB), so rank r owns the contiguous
 is an optional all-gather of the output slabs (NCCL over NVLink on GPUs; gloo in the CPU tests).
 Stage 1 (SH matrices) is recomputed on every rank -- microseconds, cheaper than a broadcast.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def shard_bins(F, world_size, rank):
@@ -122,6 +126,7 @@ class OverlappedPwd:
             self.peers = map_peer_buffers(self.buf, group=group)
             self.push_streams = [torch.cuda.Stream(device=dev) if r != self.rank else None for r in range(self.world)]
             self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._lib = _lib.require_cuda()
 
     def block_start(self, piece, rank=None):
         return (piece * self.world + (self.rank if rank is None else rank)) * self.cb
@@ -146,12 +151,16 @@ class OverlappedPwd:
             ev = torch.cuda.Event()
             ev.record()
             mine = self.buf[f0:f0 + cb]
+            nbytes = mine.numel() * mine.element_size()
+            off = mine.data_ptr() - self.buf.data_ptr()
             for k in range(1, W):                              # staggered: rank r starts with peer r + 1
                 r = (self.rank + k) % W
                 s = self.push_streams[r]
                 s.wait_event(ev)
-                with torch.cuda.stream(s):
-                    self.peers[r][f0:f0 + cb].copy_(mine, non_blocking=True)
+                # cudaMemcpyPeerAsync on this device's stream s: copy engines, no kernel
+                _lib.check(self._lib.sfa_peer_copy(ctypes.c_void_p(self.peers[r].data_ptr() + off),
+                                                   self.peers[r].device.index, ctypes.c_void_p(mine.data_ptr()),
+                                                   self.buf.device.index, nbytes, ctypes.c_void_p(s.cuda_stream)))
         for s in self.push_streams:
             if s is not None:
                 cur.wait_stream(s)

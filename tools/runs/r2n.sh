@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_fft.py -m gpu -x -q > gpurun_out/r2n_tests.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2n_tests.log
+tail -4 gpurun_out/r2n_tests.log
+timeout 300 python tools/fft_bench.py > gpurun_out/r2n_fft_bench.log 2>&1
+cat gpurun_out/r2n_fft_bench.log
+timeout 900 python tools/kloop_block_probe.py > gpurun_out/r2n_kloop_block.log 2>&1
+cat gpurun_out/r2n_kloop_block.log

@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_fft.py -m gpu -x -q > gpurun_out/r2p_tests.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2p_tests.log
+tail -4 gpurun_out/r2p_tests.log
+timeout 300 python tools/fft_bench.py > gpurun_out/r2p_fft_bench.log 2>&1
+cat gpurun_out/r2p_fft_bench.log
