@@ -475,8 +475,25 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
     int form = s->form;
     if (form == 0) {
         const double nb = 64.0;      // compare per 64 bins (the folded K-loop tiles span several bins)
-        const double c1 = gemm_cost((double)s->L, (double)s->T, (double)s->Q, nb, false) +
-                          nb * (double)s->L * p->Qp * (16.0 * 2.0 / 6.0e12 + 8.0 * s->Cd / 40e12);
+        double c1 = gemm_cost((double)s->L, (double)s->T, (double)s->Q, nb, false) +
+                    nb * (double)s->L * p->Qp * (16.0 * 2.0 / 6.0e12 + 8.0 * s->Cd / 40e12);
+        if (c64 && pwd_fused_supported(s->L, s->Q, s->T, s->Cd, p->Old, nullptr)) {
+            // fused persistent kernel: no steering slabs; 128-row tiles (pairs: an odd tile count costs a ghost
+            // tile, a tail of <= 16 rows is free), 64-frame steps, the build on the CUDA cores beside the MMAs
+            long long lt = (s->L % 128 != 0 && s->L % 128 <= 16 && s->L > 128) ? s->L / 128 : ceil_div(s->L, 128);
+            if (lt >= 2) lt = round_up(lt, 2);
+            const double rows = (double)lt * 128.0;
+            const double mma = rows * ceil(s->T / 64.0) * 64.0 * ceil(s->Q / 8.0) * 8.0 * 8.0 * 3.0 / 600e12;
+            // the builders stream rows x Qp x Cd group products (8 B each) out of L2 per bin: with many groups and
+            // few frames (cfg 2: 33 groups, T = 256) that stream, not the MMAs, sets the pace (measured 0.60 ms
+            // against 0.31 ms for the factored form)
+            const double build_fma = rows * p->Qp * s->Cd * 8.0 / 30e12;
+            const double build_l2 = rows * p->Qp * s->Cd * 8.0 / 2.5e12;
+            const double build = build_fma > build_l2 ? build_fma : build_l2;
+            const double bytes = (double)s->L * s->T * 8.0 / 4.5e12;
+            const double t = (mma > bytes ? mma : bytes);
+            c1 = nb * (t > build ? t : build);
+        }
         const double c2 = gemm_cost((double)s->M, (double)s->T, (double)s->Q, nb, true) +
                           gemm_cost((double)s->L, (double)s->T, (double)s->M, nb, true);
         form = (c1 <= c2 && s->Cd <= 64) ? 1 : 2;

@@ -132,7 +132,7 @@ struct Params {
     long long Lrows;             // rows per bin of the beam tensor / power map (all look directions)
     int K;                       // microphones (<= 64)
     int ksteps, kboxes;          // ceil(K/8), ceil(K/32)
-    int ngroups;                 // columns of d (<= NG)
+    int ngroups;                 // columns of d (<= NG; any number up to 64 for NG = 0)
     const float4* G2;            // [ltiles][ngroups][Kh][128] : (G[g][l][2j], G[g][l][2j+1]) per lane l
     int Kh;                      // ksteps * 4 column pairs
     const float2* d;             // [F][ngroups] complex64
@@ -408,39 +408,48 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             int lt;
             decode(grp, f, lt);
             if (lt >= prm.ltiles) continue;
-            float2 dg[NG];
-#pragma unroll
-            for (int g = 0; g < NG; ++g)
-                dg[g] = (g < prm.ngroups) ? __ldg(prm.d + f * prm.ngroups + g) : make_float2(0.f, 0.f);
             float are[32], aim[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) are[j] = aim[j] = 0.f;
             const float4* gp = prm.G2 + ((size_t)lt * prm.ngroups * prm.Kh + (size_t)half * 16) * kTileL + row;
+            // one group: are/aim += d_f[g] * G_g[row, this warp's 32 mic columns]
+            auto add_group = [&](const float2 dgv, const float4* gg) {
+                // all 16 loads of the group are issued before the first FMA (memory-level parallelism)
+                float4 v[16];
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                if (g < prm.ngroups && !(prm.debug & 2)) {
-                    const float4* gg = gp + (size_t)g * prm.Kh * kTileL;
-                    // all 16 loads of the group are issued before the first FMA (memory-level parallelism)
-                    float4 v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
+                for (int j = 0; j < 16; ++j)
 #if SFA_FUSED_G2_HINT
-                        v[j] = (j < npairs) ? ldg_hint(gg + (size_t)j * kTileL, g2_pol) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[j] = (j < npairs) ? ldg_hint(gg + (size_t)j * kTileL, g2_pol) : make_float4(0.f, 0.f, 0.f, 0.f);
 #else
-                        v[j] = (j < npairs) ? __ldg(gg + (size_t)j * kTileL) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[j] = (j < npairs) ? __ldg(gg + (size_t)j * kTileL) : make_float4(0.f, 0.f, 0.f, 0.f);
 #endif
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        are[2 * j] = fmaf(dg[g].x, v[j].x, are[2 * j]);
-                        are[2 * j] = fmaf(-dg[g].y, v[j].y, are[2 * j]);
-                        aim[2 * j] = fmaf(dg[g].x, v[j].y, aim[2 * j]);
-                        aim[2 * j] = fmaf(dg[g].y, v[j].x, aim[2 * j]);
-                        are[2 * j + 1] = fmaf(dg[g].x, v[j].z, are[2 * j + 1]);
-                        are[2 * j + 1] = fmaf(-dg[g].y, v[j].w, are[2 * j + 1]);
-                        aim[2 * j + 1] = fmaf(dg[g].x, v[j].w, aim[2 * j + 1]);
-                        aim[2 * j + 1] = fmaf(dg[g].y, v[j].z, aim[2 * j + 1]);
-                    }
+                for (int j = 0; j < 16; ++j) {
+                    are[2 * j] = fmaf(dgv.x, v[j].x, are[2 * j]);
+                    are[2 * j] = fmaf(-dgv.y, v[j].y, are[2 * j]);
+                    aim[2 * j] = fmaf(dgv.x, v[j].y, aim[2 * j]);
+                    aim[2 * j] = fmaf(dgv.y, v[j].x, aim[2 * j]);
+                    are[2 * j + 1] = fmaf(dgv.x, v[j].z, are[2 * j + 1]);
+                    are[2 * j + 1] = fmaf(-dgv.y, v[j].w, are[2 * j + 1]);
+                    aim[2 * j + 1] = fmaf(dgv.x, v[j].w, aim[2 * j + 1]);
+                    aim[2 * j + 1] = fmaf(dgv.y, v[j].z, aim[2 * j + 1]);
                 }
+            };
+            if (NG > 0) {
+                // few groups (spherical arrays: one per order): the bin's filters sit in registers, loop unrolled
+                constexpr int NGA = NG > 0 ? NG : 1;
+                float2 dg[NGA];
+#pragma unroll
+                for (int g = 0; g < NGA; ++g)
+                    dg[g] = (g < prm.ngroups) ? __ldg(prm.d + f * prm.ngroups + g) : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int g = 0; g < NGA; ++g)
+                    if (g < prm.ngroups && !(prm.debug & 2)) add_group(dg[g], gp + (size_t)g * prm.Kh * kTileL);
+            } else {
+                // many groups (circular arrays: one per column, up to 64): plain loop
+#pragma unroll 1
+                for (int g = 0; g < prm.ngroups; ++g)
+                    add_group(__ldg(prm.d + f * prm.ngroups + g), gp + (size_t)g * prm.Kh * kTileL);
             }
             // the MMAs of the previous task must have finished reading the operand columns
             mbar_wait(&bars->a_empty, a_phase ^ 1);
@@ -900,7 +909,7 @@ __global__ void group_products_g2_kernel(const double2* __restrict__ YL, const d
 // ------------------------------------------------------------------ host side
 bool pwd_fused_supported(long long L, long long Q, long long T, int Cd, long long out_ld, const void* out) {
     (void)L;
-    return !options().no_fused && Q >= 1 && Q <= fused::kMaxK && Cd >= 1 && Cd <= 16 && T >= 1 &&
+    return !options().no_fused && Q >= 1 && Q <= fused::kMaxK && Cd >= 1 && Cd <= 64 && T >= 1 &&
            (out_ld & 1) == 0 && (((uintptr_t)out) & 15) == 0;
 }
 
@@ -1064,9 +1073,12 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     if (Cd <= 9) {
         if (hybrid) SFA_FUSED_LAUNCH(true, 9);
         else SFA_FUSED_LAUNCH(false, 9);
-    } else {
+    } else if (Cd <= 16) {
         if (hybrid) SFA_FUSED_LAUNCH(true, 16);
         else SFA_FUSED_LAUNCH(false, 16);
+    } else {
+        if (hybrid) SFA_FUSED_LAUNCH(true, 0);
+        else SFA_FUSED_LAUNCH(false, 0);
     }
 #undef SFA_FUSED_LAUNCH
     if (le != cudaSuccess) {

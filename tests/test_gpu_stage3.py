@@ -360,17 +360,25 @@ def test_pwd_fused_kernel_shapes(mic, precision):
             pm = cpu(plan.power)
             assert pm.shape == pm_ref.shape
             assert np.max(np.abs(pm - pm_ref) / np.max(pm_ref, axis=1, keepdims=True)) < 1e-5, (N, Q, L, F, T, nofused)
-    # per-column filters (circular array: d has M = 2N+1 columns, every column its own group)
-    N, Q, L, F, T = 6, 13, 200, 6, 96
-    pol = np.linspace(0, 2 * np.pi, Q, endpoint=False)
-    poll = np.linspace(0, 2 * np.pi, L, endpoint=False)
-    Pp, Pq = O.cht_matrix(N, pol, np.full(Q, 1.0 / Q)), O.cht_matrix(N, poll)
-    k = O.wavenumbers(64)[:F] + 0.7
-    Dn, _ = O.regularize(1 / O.circular_pw(N, k, 0.1, "open"), 3000, "softclip")
-    X = (rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(np.complex64)
-    ref = O.pwd_factored(Pq, Dn, Pp, X.astype(np.complex128))
-    q = S.pwd(Pq, Dn, Pp, torch.from_numpy(X).cuda(), precision=precision, form="steering")
-    assert bin_err(cpu(q), ref) < TOL64
+    # per-column filters (circular array: d has M = 2N+1 columns, every column its own group): 13 groups (unrolled
+    # builder), 33 groups = BASELINE config 2 (N = 16, 32 mics, 360 look directions; builder loop over the groups),
+    # the latter also with enough bins for the stream-ahead conversion
+    for (N, Q, L, F, T) in ((6, 13, 200, 6, 96), (16, 32, 360, 12, 256), (16, 32, 360, 200, 70), (31, 64, 150, 5, 40)):
+        pol = np.linspace(0, 2 * np.pi, Q, endpoint=False)
+        poll = np.linspace(0, 2 * np.pi, L, endpoint=False)
+        Pp, Pq = O.cht_matrix(N, pol, np.full(Q, 1.0 / Q)), O.cht_matrix(N, poll)
+        k = np.linspace(0.5, 40.0, F)
+        Dn, _ = O.regularize(1 / O.circular_pw(N, k, 0.1, "open"), 3000, "softclip")
+        X = (rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(np.complex64)
+        sel = sorted(set([0, F // 2, F - 1]))
+        ref = O.pwd_factored(Pq, Dn[sel], Pp, X[sel].astype(np.complex128))
+        plan = S.PwdPlan(Pq, Dn, Pp, T, precision=precision, form="steering")
+        q = plan(torch.from_numpy(X).cuda(), power=True)
+        assert bin_err(cpu(q[sel]), ref) < TOL64, (N, Q, L, F, T, bin_err(cpu(q[sel]), ref))
+        pm_ref = np.mean(np.abs(ref) ** 2, axis=2)
+        assert np.max(np.abs(cpu(plan.power)[sel] - pm_ref) / np.max(pm_ref, axis=1, keepdims=True)) < 1e-5
+        q_auto = S.pwd(Pq, Dn, Pp, torch.from_numpy(X).cuda(), precision=precision)       # form chosen by the plan
+        assert bin_err(cpu(q_auto[sel]), ref) < TOL64
 
 
 @pytest.mark.parametrize("precision", ["c64_fast", "c64"])
