@@ -404,6 +404,118 @@ zgemm_kernel(long long B, long long Nn, long long Mm, long long K, const double2
     }
 }
 
+// The same product on the FP64 tensor cores: mma.sync.m8n8k4.f64 (DMMA), four real products per complex
+// one.  CTA tile 64 (n) x 64 (m), eight warps as 2 (n) x 4 (m), warp tile 32 x 16 = 4 x 2 DMMA tiles with (Re, Im)
+// accumulators; k advances 16 per step.  Operands are staged in shared memory as separate Re / Im planes whose
+// pitches (20 and 68 doubles) make every fragment load conflict-free (lane (g, t) of a half-warp hits bank
+// 4 g + t); the global loads of k-tile i + 1 are in registers while tile i is multiplied.
+// A fragment a0: row g = lane / 4, col t = lane % 4;  B fragment b0: row t, col g;  C fragment: row g, cols 2t, 2t+1.
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256)
+zgemm_dmma_kernel(long long B, long long Nn, long long Mm, long long K, const double2* __restrict__ P, long long ldP,
+                  long long strideP, const double2* __restrict__ R, long long ldR, long long strideR,
+                  double2* __restrict__ out, long long ldo, long long strideO, const double2* __restrict__ rowscale,
+                  long long strideS) {
+    constexpr int TM = 64, TN = 64, TK = 16, PP = 20, PR = 68;
+    __shared__ double Pre[TN * PP], Pim[TN * PP];          // [n][k]
+    __shared__ double Rre[TK * PR], Rim[TK * PR];          // [k][m]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wn = (warp >> 2) * 32, wm = (warp & 3) * 16;  // warp tile origin inside the CTA tile
+    const long long m_tiles = (Mm + TM - 1) / TM, n_tiles = (Nn + TN - 1) / TN;
+    const long long tiles = B * m_tiles * n_tiles;
+    // global -> register staging: thread loads 4 elements of the P tile ([64 n][16 k]) and 4 of the R tile ([16 k][64 m])
+    const int pn = threadIdx.x >> 2, pk = (threadIdx.x & 3) * 4;         // P: row pn, k = pk .. pk + 3
+    const int rk = threadIdx.x >> 4, rm = (threadIdx.x & 15) * 4;        // R: row rk, m = rm .. rm + 3
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long b = tile / (m_tiles * n_tiles);
+        const long long rem = tile - b * m_tiles * n_tiles;
+        const long long nt = rem / m_tiles, mt = rem - nt * m_tiles;
+        const long long m0 = mt * TM, n0 = nt * TN;
+        const double2* Pb = P + b * strideP;
+        const double2* Rb = R + b * strideR;
+        double acr[4][2][2], aci[4][2][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acr[i][j][0] = acr[i][j][1] = aci[i][j][0] = aci[i][j][1] = 0.0;
+        double2 pv[4], rv[4];
+        auto fetch = [&](long long k0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const long long n = n0 + pn, k = k0 + pk + e;
+                pv[e] = (n < Nn && k < K) ? __ldg(Pb + n * ldP + k) : make_double2(0.0, 0.0);
+                const long long kk = k0 + rk, m = m0 + rm + e;
+                rv[e] = (kk < K && m < Mm) ? __ldg(Rb + kk * ldR + m) : make_double2(0.0, 0.0);
+            }
+        };
+        fetch(0);
+        for (long long k0 = 0; k0 < K; k0 += TK) {
+            __syncthreads();                                // the previous tile's fragments have been read
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                Pre[pn * PP + pk + e] = pv[e].x;
+                Pim[pn * PP + pk + e] = pv[e].y;
+                Rre[rk * PR + rm + e] = rv[e].x;
+                Rim[rk * PR + rm + e] = rv[e].y;
+            }
+            __syncthreads();
+            if (k0 + TK < K) fetch(k0 + TK);                // in flight during the multiplications below
+#pragma unroll
+            for (int ks = 0; ks < TK; ks += 4) {
+                double are[4], aim[4], nim[4], bre[2], bim[2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    are[i] = Pre[(wn + 8 * i + g) * PP + ks + t];
+                    aim[i] = Pim[(wn + 8 * i + g) * PP + ks + t];
+                    nim[i] = -aim[i];
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    bre[j] = Rre[(ks + t) * PR + wm + 8 * j + g];
+                    bim[j] = Rim[(ks + t) * PR + wm + 8 * j + g];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        dmma(acr[i][j], are[i], bre[j]);
+                        dmma(acr[i][j], nim[i], bim[j]);
+                        dmma(aci[i][j], are[i], bim[j]);
+                        dmma(aci[i][j], aim[i], bre[j]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long n = n0 + wn + 8 * i + g;
+            if (n >= Nn) continue;
+            double2 sc = make_double2(1.0, 0.0);
+            if (rowscale) sc = rowscale[b * strideS + n];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const long long m = m0 + wm + 8 * j + 2 * t + e;
+                    if (m >= Mm) continue;
+                    double xr = acr[i][j][e], xi = aci[i][j][e];
+                    if (rowscale) {
+                        const double tr = xr * sc.x - xi * sc.y;
+                        xi = xr * sc.y + xi * sc.x;
+                        xr = tr;
+                    }
+                    out[b * strideO + n * ldo + m] = make_double2(xr, xi);
+                }
+            }
+        }
+    }
+}
+
 __global__ void conj_transpose_kernel(const double2* __restrict__ S, long long rows, long long cols,
                                       double2* __restrict__ out) {   // out[c][r] = conj(S[r][c])
     const long long total = rows * cols;
@@ -617,6 +729,20 @@ static int pwd_prepare(const sfa_pwd_shape* s, const Plan& p, const double2* yl,
     return SFA_OK;
 }
 
+static unsigned zgrid(long long tiles);
+// FP64 complex GEMM launch: DMMA kernel unless switched off ("no_dmma": the CUDA-core FMA tile kernel)
+static int launch_zgemm(long long B, long long Nn, long long Mm, long long K, const double2* P, long long ldP,
+                        long long strideP, const double2* R, long long ldR, long long strideR, double2* out,
+                        long long ldo, long long strideO, const double2* rowscale, long long strideS, cudaStream_t st) {
+    const unsigned grid = zgrid(B * ceil_div(Mm, 64) * ceil_div(Nn, 64));
+    if (options().no_dmma)
+        zgemm_kernel<<<grid, 256, 0, st>>>(B, Nn, Mm, K, P, ldP, strideP, R, ldR, strideR, out, ldo, strideO, rowscale, strideS);
+    else
+        zgemm_dmma_kernel<<<grid, 256, 0, st>>>(B, Nn, Mm, K, P, ldP, strideP, R, ldR, strideR, out, ldo, strideO, rowscale,
+                                               strideS);
+    SFA_LAUNCH_CHECK();
+    return SFA_OK;
+}
 static unsigned zgrid(long long tiles) { return (unsigned)(tiles < 65535LL * 16 ? tiles : 65535LL * 16); }
 
 // Bins [0, nf) of d / X / out (pointers already offset to the first bin); nf <= p.fc.
@@ -667,23 +793,16 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
         double2* A = reinterpret_cast<double2*>(w + p.off_A);
         steer_build_f64_kernel<<<grid1d(LQ * nf), 256, 0, st>>>(G, dd, Cd, Cd, 0, (int)nf, LQ, A);
         SFA_LAUNCH_CHECK();
-        zgemm_kernel<<<zgrid(nf * ceil_div(T, 64) * ceil_div(L, 64)), 256, 0, st>>>(
-            nf, L, T, Q, A, p.Qp, LQ, x, T, Q * T, o, p.Old, L * p.Old, nullptr, 0);
-        SFA_LAUNCH_CHECK();
-        return SFA_OK;
+        return launch_zgemm(nf, L, T, Q, A, p.Qp, LQ, x, T, Q * T, o, p.Old, L * p.Old, nullptr, 0, st);
     }
     const double2* P1 = reinterpret_cast<const double2*>(w + p.off_P1);      // conj(Y_Q)^T [M][Q]
     double2* dcols = reinterpret_cast<double2*>(w + p.off_dcols);
     double2* Z = reinterpret_cast<double2*>(w + p.off_Z);
     expand_diag_kernel<double2><<<grid1d(nf * M), 256, 0, st>>>(dd, nf, Cd, M, s->d_is_per_order, dcols);
     SFA_LAUNCH_CHECK();
-    zgemm_kernel<<<zgrid(nf * ceil_div(T, 64) * ceil_div(M, 64)), 256, 0, st>>>(
-        nf, M, T, Q, P1, Q, 0, x, T, Q * T, Z, p.Tld, (long long)M * p.Tld, dcols, M);
-    SFA_LAUNCH_CHECK();
-    zgemm_kernel<<<zgrid(nf * ceil_div(T, 64) * ceil_div(L, 64)), 256, 0, st>>>(
-        nf, L, T, M, yl, M, 0, Z, p.Tld, (long long)M * p.Tld, o, p.Old, L * p.Old, nullptr, 0);
-    SFA_LAUNCH_CHECK();
-    return SFA_OK;
+    rc = launch_zgemm(nf, M, T, Q, P1, Q, 0, x, T, Q * T, Z, p.Tld, (long long)M * p.Tld, dcols, M, st);
+    if (rc != SFA_OK) return rc;
+    return launch_zgemm(nf, L, T, M, yl, M, 0, Z, p.Tld, (long long)M * p.Tld, o, p.Old, L * p.Old, nullptr, 0, st);
 }
 
 // Form 1, several chunks: the (HBM-store-bound) steering-matrix build of chunk i+1 is issued on a

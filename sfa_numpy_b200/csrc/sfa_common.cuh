@@ -70,6 +70,7 @@ struct Options {
     int old_build;         // steering build: generic kernel instead of the few-groups fast kernel
     int no_fused;          // steering form: slab build + GEMM launches instead of the fused persistent kernel
     int fused_prepass;     // fused kernel: split ALL spectra in the pre-pass kernel (no in-kernel stream-ahead conversion)
+    int no_dmma;           // complex128 path: CUDA-core FMA tile kernel instead of the FP64 tensor-core (DMMA) kernel
     int fft_generic;       // irfft / stft: the generic radix-4 ping-pong kernel instead of the radix-16 fast path
     int reserve_sms;       // SMs the persistent tensor-core kernels leave free (for NCCL's copy kernels when a collective
                            // is meant to run under them)

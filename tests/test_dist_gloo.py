@@ -106,6 +106,12 @@ def _overlap_worker(rank, world, port, results):
         assert sorted(b for o in owners for b in o) == list(range(F))
         with pytest.raises(ValueError):
             sd.OverlappedPwd(Y_look, dn[:10], Y_mic, T, pieces=pieces, make_plan=lambda *a: None)
+        with pytest.raises(ValueError):                      # peer-to-peer pushes need CUDA devices
+            sd.OverlappedPwd(Y_look, dn, Y_mic, T, pieces=pieces, transport="p2p",
+                             make_plan=lambda yl, d, ym, t: (_TorchPlan(yl, d, ym, t), torch.device("cpu"),
+                                                             torch.complex128, t + 2))
+        with pytest.raises(ValueError):
+            sd.OverlappedPwd(Y_look, dn, Y_mic, T, pieces=pieces, transport="carrier pigeon", make_plan=lambda *a: None)
         results[rank] = True
     finally:
         dist.destroy_process_group()
