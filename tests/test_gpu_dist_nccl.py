@@ -80,3 +80,44 @@ def test_nccl_world2_sharded_pwd():
     results = mgr.dict()
     mp.spawn(_worker, args=(2, port, results), nprocs=2, join=True)
     assert results.get(0) and results.get(1)
+
+
+def test_two_devices_in_one_process():
+    """One process driving two GPUs (function attributes such as the dynamic shared-memory opt-in are per
+    device): every kernel family runs on cuda:1 after it has run on cuda:0, and the results agree bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import sfa_numpy_b200 as micarray
+    from oracle import sfa_oracle as O
+    A, R, S = micarray.modal.angular, micarray.modal.radial, micarray.modal.steering
+    res = []
+    for dev in ("cuda:0", "cuda:1"):
+        d = torch.device(dev)
+        out = {}
+        # fused steering kernel (> 48 KB dynamic shared memory), stream-ahead path included (many bins)
+        N, Q, L, F, T = 3, 16, 389, 260, 100
+        az, co, w = O.fibonacci_grid(Q)
+        azl, col, _ = O.fibonacci_grid(L)
+        Y_p = A.sht_matrix(N, torch.from_numpy(az).to(d), torch.from_numpy(co).to(d), torch.from_numpy(w).to(d))
+        Y_q = A.sht_matrix(N, torch.from_numpy(azl).to(d), torch.from_numpy(col).to(d))
+        k = torch.from_numpy(np.linspace(0.5, 40.0, F)).to(d)
+        _, dn, _ = R.radial_filters(N, k, 0.042, "rigid", 100.0, "Tikh")
+        X = torch.from_numpy(O.synth_spectra(F, Q, T, seed=2)).to(d)
+        assert Y_p.device == d and dn.device == d
+        out["fused"] = S.pwd(Y_q, dn, Y_p, X, precision="c64_fast", form="steering").cpu()
+        # K-loop kernel (K > 64) and the resident-K kernel (factored form), FP64 path, cht rows kernel, FFT fast path
+        N2, Q2 = 9, 100
+        az2, co2, w2 = O.fibonacci_grid(Q2)
+        Yp2 = A.sht_matrix(N2, torch.from_numpy(az2).to(d), torch.from_numpy(co2).to(d), torch.from_numpy(w2).to(d))
+        Yq2 = A.sht_matrix(N2, torch.from_numpy(azl).to(d), torch.from_numpy(col).to(d))
+        _, dn2, _ = R.radial_filters(N2, k[:8], 0.1, "rigid", 100.0, "Tikh")
+        X2 = torch.from_numpy(O.synth_spectra(8, Q2, 40, seed=3)).to(d)
+        out["kloop"] = S.pwd(Yq2, dn2, Yp2, X2, precision="c64", form="factored").cpu()
+        out["c128"] = S.pwd(Yq2, dn2, Yp2, X2.to(torch.complex128), precision="c128").cpu()
+        out["cht"] = A.cht_matrix(14, torch.linspace(0, 6.28, 5000, dtype=torch.float64, device=d)).cpu()
+        out["irfft"] = micarray.fft.irfft(out["fused"][:129, :3, :].to(d).contiguous(), n=256, shift=True).cpu()
+        torch.cuda.synchronize(d)
+        res.append(out)
+    for key in res[0]:
+        assert torch.equal(res[0][key], res[1][key]), key
