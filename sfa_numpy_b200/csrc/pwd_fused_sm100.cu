@@ -76,6 +76,11 @@ constexpr int kStoreRing = SFA_FUSED_RING;          // staging slots (one pass =
 // group-product table and the spectra planes (both re-read by every task of a bin) out of L2 -- measured on the
 // headline shape: 4.99 -> 4.64 ms per step.  (evict_last on the table loads alone gives 4.72 ms and adds
 // nothing on top; a third staging slot per epilogue warp costs 4 %.)
+// Store path: a pure-store kernel with this row-tile pattern moves 4.95 TB/s through tensor-map boxes and 6.1 TB/s
+// through one 1-D bulk copy per 512-byte row piece (tools/store_probe3.cu, store_probe4.cu) -- but a bulk copy
+// costs its issuing lane ~95 cycles, so the 64 copies per warp and frame tile that the epilogue would need take
+// longer than the tile itself (measured in this kernel: 13.0 ms per step against 5.45 ms); one tensor-map store
+// moves 32 row pieces per instruction and stays.
 #ifndef SFA_FUSED_G2_HINT
 #define SFA_FUSED_G2_HINT 0
 #endif
