@@ -92,17 +92,25 @@ class OverlappedPwd:
                 PUSHES its finished block into each peer with DMA copies (copy engines over NVLink /
                 NVSwitch, one stream per peer).  No SM is involved, so the transfer of piece c really runs under
                 the kernels of piece c + 1.  A one-element all-reduce at both ends of a call orders the pushes
-                against the peers' use of their buffers.
+                against the peers' use of their buffers.  Every block leaves the GPU N - 1 times, though: at 8 GPUs
+                the pushes reach 400 GB/s per GPU where NCCL (one send through the switch) reaches 560-650;
+      "auto" -- "p2p" for two ranks on GPUs, "nccl" otherwise.
 
     `compute(plan, X_piece, out_piece)` may be injected (the CPU/gloo test of the scheduling logic does)."""
 
     def __init__(self, Y_look, dn, Y_mic, T, pieces=4, precision="c64_fast", form="auto", group=None, make_plan=None,
                  device=None, transport="nccl"):
-        if transport not in ("nccl", "p2p"):
-            raise ValueError("transport must be 'nccl' or 'p2p'")
-        self.transport = transport
+        if transport not in ("nccl", "p2p", "auto"):
+            raise ValueError("transport must be 'nccl', 'p2p' or 'auto'")
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if transport == "auto":
+            # measured on 8 x B200 (cfg 5): pushes win while a rank has one or two peers (2 GPUs: 38.9 against
+            # 50.1 ms); from four GPUs on every block leaves a rank N - 1 times while NCCL sends it once through
+            # the switch (8 GPUs: 26.7 ms with NCCL against 38.0 ms)
+            on_gpu = (device is not None and torch.device(device).type == "cuda") or (device is None and dn.is_cuda)
+            transport = "p2p" if (on_gpu and self.world == 2) else "nccl"
+        self.transport = transport
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         F = dn.shape[0]
         if F % (self.world * pieces):
