@@ -727,6 +727,17 @@ def main():
         pm_ms = timed(lambda: S.power_map(bf.out))
         line["collective"] = {"power_map_kernel_ms": pm_ms, "power_map_read_GBps": 8.0 * nb * L * T / (pm_ms * 1e-3) / 1e9,
                               "note": "single GPU: no collective; at N > 1 the map comes out of the fused kernel's epilogue"}
+        try:
+            # the beam-map product alone: stage 3 with the power map accumulated in the epilogue and NO beam stores
+            # (the beams exist in tensor memory only) -- the tensor-issue side of the kernel without its HBM side
+            pm_t = torch.empty((nb, L), dtype=torch.float32, device=dev)
+            mo_ms = timed(lambda: bf.plan(bf.X, power=pm_t, beams=False), n=5)
+            line["power_map_only"] = {"ms": mo_ms, "outputs_per_s": F * L * T / (mo_ms * 1e-3),
+                                      "api": "PwdPlan(X, power=..., beams=False): stage 3 only, beams never written",
+                                      "alg_tflops": 8.0 * nb * L * Q * T / (mo_ms * 1e-3) / 1e12}
+        except Exception as e:
+            line["power_map_only"] = {"error": repr(e)}
+            torch.cuda.synchronize()
 
     # ---- e2e through the host-buffer C ABI: every rank pushes ITS SLAB of the problem through its own PCIe link.
     #      The timed region covers stages 1-2 on the device, the hand-over of the operators to the host context

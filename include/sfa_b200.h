@@ -190,11 +190,14 @@ int sfa_pwd_apply(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* Y
  *   sfa_pwd_run      q = ... for the current d and X, reading the prepared `work` (same shape, same work buffer).
  * `power` (nullable, complex64 precisions only): additionally writes the beam power map mean_t |q[f,l,t]|^2 as
  * float32 [F, L] (see sfa_power_map).  The fused steering kernel accumulates it in its epilogue -- a CTA owns
- * whole rows of q -- so it costs no extra pass over the beams; other paths append one sfa_power_map pass. */
+ * whole rows of q -- so it costs no extra pass over the beams; other paths append one sfa_power_map pass.
+ * With out == NULL and a `power` pointer only the map is produced: the fused kernel skips its stores and the beams
+ * never leave tensor memory (SFA_ERR_UNSUPPORTED for plans that are not the fused kernel; sfa_pwd_is_fused tells). */
 int sfa_pwd_prepare(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* Y_Q, void* work, size_t work_bytes,
                     void* stream);
 int sfa_pwd_run(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* d, const void* X, void* out,
                 float* power, void* work, size_t work_bytes, void* stream);
+int sfa_pwd_is_fused(const sfa_pwd_shape* s);
 
 /* Batched complex GEMM building block used by sfa_pwd_apply, exposed for tests:
  *   out[b, n, m] = sum_k P[b?, n, k] * R[b, k, m]  (* rowscale[b, n] if given)

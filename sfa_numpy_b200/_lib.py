@@ -57,6 +57,7 @@ SIGNATURES = {
     "sfa_pwd_apply": (c_int, [ctypes.POINTER(PwdShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_void_p]),
     "sfa_pwd_prepare": (c_int, [ctypes.POINTER(PwdShape), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sfa_pwd_is_fused": (c_int, [ctypes.POINTER(PwdShape)]),
     "sfa_pwd_run": (c_int, [ctypes.POINTER(PwdShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_size_t, c_void_p]),
     "sfa_cgemm3x": (c_int, [c_int64] * 4 + [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,

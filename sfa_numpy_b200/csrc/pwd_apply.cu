@@ -757,7 +757,7 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
         const float2* x = reinterpret_cast<const float2*>(X);
         float2* o = reinterpret_cast<float2*>(out);
         if (p.fused) {
-            if (((uintptr_t)out) & 15) return SFA_ERR_INVALID;
+            if (((uintptr_t)out) & 15) return SFA_ERR_INVALID;              // (a null `out` = power map only)
             float2* dF = reinterpret_cast<float2*>(w + p.off_dF);
             d_to_float_kernel<<<grid1d(nf * Cd), 256, 0, st>>>(dd, nf * Cd, dF);
             SFA_LAUNCH_CHECK();
@@ -894,14 +894,24 @@ extern "C" int sfa_pwd_prepare(const sfa_pwd_shape* s, const sfa_c128* Y_L, cons
                        (cudaStream_t)stream);
 }
 
+// 1 when the plan for this shape is the fused persistent steering kernel (power map in the epilogue, map-only runs)
+extern "C" int sfa_pwd_is_fused(const sfa_pwd_shape* s) {
+    Plan p;
+    if (make_plan(s, &p) != SFA_OK) return 0;
+    return p.fused;
+}
+
 extern "C" int sfa_pwd_run(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sfa_c128* d, const void* X, void* out,
                            float* power, void* work, size_t work_bytes, void* stream) {
     Plan p;
     int rc = make_plan(s, &p);
     if (rc != SFA_OK) return rc;
     if (s->F == 0) return SFA_OK;
-    if (!Y_L || !d || !X || !out || !work) return SFA_ERR_INVALID;
+    if (!Y_L || !d || !X || !work) return SFA_ERR_INVALID;
     if (power && !is_c64(s)) return SFA_ERR_UNSUPPORTED;
+    // out == NULL: only the beam power map is wanted.  The fused steering kernel then skips its stores (the beams
+    // exist in tensor memory only); no other path can do that.
+    if (!out && !(power && p.fused)) return SFA_ERR_UNSUPPORTED;
     if (work_bytes < p.total) return SFA_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
@@ -915,7 +925,7 @@ extern "C" int sfa_pwd_run(const sfa_pwd_shape* s, const sfa_c128* Y_L, const sf
             const long long nf = (s->F - f0 < p.fc) ? (s->F - f0) : p.fc;
             rc = pwd_run_bins(s, p, nf, yl, dd + f0 * s->Cd,
                               reinterpret_cast<const unsigned char*>(X) + (size_t)f0 * s->Q * s->T * eb,
-                              reinterpret_cast<unsigned char*>(out) + (size_t)f0 * s->L * p.Old * eb, w, st,
+                              out ? reinterpret_cast<unsigned char*>(out) + (size_t)f0 * s->L * p.Old * eb : nullptr, w, st,
                               (power && p.fused) ? power + f0 * s->L : nullptr);
         }
     }

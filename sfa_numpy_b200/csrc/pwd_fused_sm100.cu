@@ -81,6 +81,11 @@ constexpr int kStoreRing = SFA_FUSED_RING;          // staging slots (one pass =
 // costs its issuing lane ~95 cycles, so the 64 copies per warp and frame tile that the epilogue would need take
 // longer than the tile itself (measured in this kernel: 13.0 ms per step against 5.45 ms); one tensor-map store
 // moves 32 row pieces per instruction and stays.
+// the converters run ahead until the plane ring is full and then wait for a slot most of the time: a slot frees
+// every ~20 us, so the poll can be slow
+#ifndef SFA_FUSED_RING_SLEEP
+#define SFA_FUSED_RING_SLEEP 2000
+#endif
 #ifndef SFA_FUSED_G2_HINT
 #define SFA_FUSED_G2_HINT 0
 #endif
@@ -145,6 +150,7 @@ struct Params {
     long long groups;            // F * lt_groups
     float* power;                // nullable: [F][L] mean_t |q|^2, accumulated in the epilogue (a CTA owns whole rows)
     int store_evict_first;       // beam stores with the L2 evict_first policy (output much larger than L2)
+    int no_store;                // power map only: the beams are not written (out == nullptr)
     // stream-ahead conversion of the spectra by the two spare warps of every CTA (conv_D = 0: all done by the pre-pass)
     int conv_D;                  // task on bin f converts one slice of bin f + conv_D; bins < conv_D come from the pre-pass
     int nsl;                     // slices per bin = lt_groups * csize (one per CTA-task of a bin)
@@ -534,6 +540,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                             }
                         }
                     }
+                    if (prm.no_store) continue;                                 // power map only (warp-uniform)
                     unsigned char* const sbuf = my_store + (size_t)buf * 2 * kStoreBoxBytes;
                     // the stores issued from this slot kStoreRing passes ago must have finished reading it
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStoreRing - 1) : "memory");
@@ -625,7 +632,7 @@ __device__ __forceinline__ void convert_slice(const Params& prm, unsigned char* 
         // the slot still holds bin fc - ring until every task of that bin has received its planes (two rounds of
         // tasks ago in the normal course of events, so this does not spin)
         if (tid == 0)
-            while (ld_acquire_gpu(prm.done + (fc - prm.ring)) < prm.nsl) __nanosleep(64);
+            while (ld_acquire_gpu(prm.done + (fc - prm.ring)) < prm.nsl) __nanosleep(SFA_FUSED_RING_SLEEP);
         named_bar_sync(1, 64);
     }
     if (rem > 0) {
@@ -703,7 +710,7 @@ __device__ __forceinline__ void convert_slice(const Params& prm, unsigned char* 
             }
             float p = 0.f;
             if (t < T) {
-                prm.out[(fc * prm.Lrows + prm.Lm + r) * prm.ldo + t] = make_float2(ar, ai);
+                if (!prm.no_store) prm.out[(fc * prm.Lrows + prm.Lm + r) * prm.ldo + t] = make_float2(ar, ai);
                 p = ar * ar + ai * ai;
             }
             if (prm.power) {
@@ -847,7 +854,7 @@ x_split_tail_kernel(const float2* __restrict__ X, int Q, long long T, int Kp, in
                 ai = fmaf(a.y, x.x, ai);
             }
             if (t < T) {
-                out[(f * L + Lm + r) * ldo + t] = make_float2(ar, ai);
+                if (out) out[(f * L + Lm + r) * ldo + t] = make_float2(ar, ai);
                 if (power) {
                     float p = ar * ar + ai * ai;
                     for (int off = 16; off; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
@@ -984,6 +991,8 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     prm.groups = nf * prm.lt_groups;
     prm.power = power;
     prm.store_evict_first = ((double)nf * (double)L * (double)ldo * 8.0 > 256e6) ? 1 : 0;     // >> L2 (126 MB)
+    prm.no_store = out ? 0 : 1;
+    if (!out && !power) return SFA_ERR_INVALID;
     const long long max_clusters = persistent_sms() / prm.csize;
     const long long n_clusters = prm.groups < max_clusters ? prm.groups : max_clusters;
     // Stream-ahead conversion: the CTAs working on bin f split the spectra of bin f + D, D = the number of bins
@@ -1036,10 +1045,12 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
             return SFA_ERR_CUDA;
         }
         // beams as fp32 [nf][L][2*ldo]; store box = 32 rows x 32 fp32 (16 frames), SWIZZLE_128B staging
+        // (power map only: the map is encoded over the plane buffer and never used)
+        void* const obase = out ? (void*)out : (void*)Xs;
         cuuint64_t odim[3] = {(cuuint64_t)(2 * T), (cuuint64_t)Lmain, (cuuint64_t)nf};
         cuuint64_t ostr[2] = {(cuuint64_t)ldo * 8, (cuuint64_t)L * ldo * 8};
         cuuint32_t obox[3] = {32, 32, 1};
-        r = encode(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)out, odim, ostr, obox, estr,
+        r = encode(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, obase, odim, ostr, obox, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {

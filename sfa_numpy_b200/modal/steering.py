@@ -230,15 +230,30 @@ class PwdPlan:
                                                 _lib.ptr(self.work), self.nbytes, _lib.stream_ptr(self.dev)))
         self._prepared_ld = self.shape.out_ld
 
-    def __call__(self, X, out=None, power=None):
+    def __call__(self, X, out=None, power=None, beams=True):
+        """``beams=False`` (with `power`): only the beam power map is produced -- the fused steering kernel skips its
+        stores, the 8 F L T bytes of beams never reach memory; returns the map.  Needs a plan that runs the fused
+        kernel (complex64 precisions, steering form, at most 64 microphones), otherwise ValueError."""
         if X.dtype != self.cdtype or not X.is_contiguous() or X.device != self.dev:
             raise ValueError("X must be a contiguous {} tensor on {}".format(self.cdtype, self.dev))
         if tuple(X.shape) != (self.out_shape[0], self._Y_mic.shape[0], self.out_shape[2]):
             raise ValueError("X must have shape (F, Q, T) = {}".format((self.out_shape[0], self._Y_mic.shape[0],
                                                                          self.out_shape[2])))
-        if out is None:
-            out = _alloc_out(*self.out_shape, self.cdtype, self.dev)
-        ld = _check_out(out, *self.out_shape, self.cdtype, self.dev)
+        if not beams:
+            if power is None or power is False:
+                raise ValueError("beams=False needs power=True or a power tensor")
+            if out is not None:
+                raise ValueError("beams=False writes no beams: do not pass out")
+            ld = _padded_pitch(self.out_shape[2])
+            probe = _lib.PwdShape.from_buffer_copy(self.shape)
+            probe.out_ld = ld
+            if not self.lib.sfa_pwd_is_fused(ctypes.byref(probe)):
+                raise ValueError("a power map without the beams needs the fused steering kernel (complex64, steering "
+                                 "form, <= 64 microphones and <= 64 filter columns)")
+        else:
+            if out is None:
+                out = _alloc_out(*self.out_shape, self.cdtype, self.dev)
+            ld = _check_out(out, *self.out_shape, self.cdtype, self.dev)
         # the plan (kernel choice, workspace layout) depends on the row pitch of `out`: prepare again if it changed
         if self._prepared_ld is None or ld != self.shape.out_ld:
             self.shape.out_ld = ld
@@ -264,7 +279,7 @@ class PwdPlan:
             _lib.check(self.lib.sfa_pwd_run(ctypes.byref(self.shape), _lib.ptr(self._Y_look), _lib.ptr(self.dn),
                                             _lib.ptr(X), _lib.ptr(out), _lib.ptr(pm), _lib.ptr(self.work),
                                             self.nbytes, _lib.stream_ptr(self.dev)))
-        return out
+        return out if beams else pm
 
 
 class PwdHost:

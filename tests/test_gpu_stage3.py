@@ -427,3 +427,31 @@ def test_pwd_fused_stream_ahead_conversion(mic, precision):
         assert bin_err(got, ref) < TOL64, (N, Q, L, F, T, bin_err(got, ref))
         pm_ref = np.mean(np.abs(ref) ** 2, axis=2)
         assert np.max(np.abs(pm_a[bins] - pm_ref) / np.max(pm_ref, axis=1, keepdims=True)) < 1e-5
+
+
+def test_pwd_power_map_only(mic):
+    """``plan(X, power=True, beams=False)``: the fused kernel skips its stores -- the map must equal the one of a run
+    that also writes the beams, bit for bit; plans that are not the fused kernel refuse."""
+    import torch
+    A, R, S = mic.modal.angular, mic.modal.radial, mic.modal.steering
+    rng = np.random.default_rng(9)
+    for (N, Q, L, F, T) in ((3, 20, 389, 260, 100), (4, 36, 300, 7, 130)):
+        az, co, w = O.fibonacci_grid(Q)
+        azl, col, _ = O.fibonacci_grid(L)
+        Yp, Yq = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
+        k = np.linspace(0.5, 40.0, F)
+        dn, _ = O.regularize(1 / O.spherical_pw(N, k, 0.042, "rigid"), 100, "Tikh")
+        X = torch.from_numpy((rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(np.complex64)).cuda()
+        plan = S.PwdPlan(Yq, dn, Yp, T, precision="c64_fast", form="steering")
+        q = plan(X, power=True)
+        pm_full = plan.power.clone()
+        plan.power.zero_()
+        pm = plan(X, power=True, beams=False)
+        assert pm is plan.power and torch.equal(pm, pm_full)
+        ref = np.mean(np.abs(cpu(q).astype(np.complex128)) ** 2, axis=2)
+        assert np.max(np.abs(cpu(pm) - ref) / np.max(ref, axis=1, keepdims=True)) < 1e-5
+        with pytest.raises(ValueError):
+            plan(X, beams=False)
+    plan = S.PwdPlan(Yq, dn, Yp, T, precision="c64_fast", form="factored")
+    with pytest.raises(ValueError):
+        plan(X, power=True, beams=False)
