@@ -850,6 +850,33 @@ def main():
                                 for k2, v in r.items()} for r in rows]
         except Exception as e:
             line["stage12"] = {"error": repr(e)}
+    if rank == 0 and not args.no_stage12:
+        # stages 1-2 of the headline config as they run inside the step: one graph launch over the four calls
+        # (2 x sht_matrix, radial filter + zero replacement) instead of four launch-latency-bound API calls
+        try:
+            d_geo12 = [torch.from_numpy(a).to(dev) for a in (azi, colat, w, azl, col, k)]
+
+            def s12():
+                A.sht_matrix(N, d_geo12[0], d_geo12[1], d_geo12[2])
+                A.sht_matrix(N, d_geo12[3], d_geo12[4])
+                R.radial_filters(N, d_geo12[5], cfg["r"], cfg["setup"], cfg["a0"], cfg["method"], check="none")
+            for _ in range(3):
+                s12()
+            torch.cuda.synchronize()
+            eager_us = timed(s12, n=20) * 1e3
+            g12 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g12):
+                s12()
+            graph_us = timed(lambda: g12.replay(), n=50) * 1e3
+            evals = (Q + L) * (N + 1) ** 2 + F * (N + 1)
+            line["stage12_graph"] = {"config": "cfg3: sht_matrix at 64 mics + 2562 look dirs, spherical_pw + regularize at 1024 bins",
+                                     "eager_us": eager_us, "graph_us": graph_us, "evals": evals,
+                                     "evals_per_s_graph": evals / (graph_us * 1e-6),
+                                     "note": "3.5 MB of output: latency-bound whatever is done; inside the step it is 1-2 % of the time"}
+            del g12
+        except Exception as e:
+            line["stage12_graph"] = {"error": repr(e)}
+            torch.cuda.synchronize()
     if rank == 0 and not args.no_other_configs and world == 1:
         for key, fn in (("tensor_bound_configs", lambda: tensor_bound_configs(torch, micarray, O, dev, args.precision, peaks)),
                         ("small_configs", lambda: small_configs(torch, micarray, O, dev, args.precision, peaks["hbm_gbs"])),

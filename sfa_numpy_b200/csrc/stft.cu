@@ -294,7 +294,10 @@ stft_kernel(const StftParams prm, const R* __restrict__ x, const R* __restrict__
 // ------------------------------------------------------------------------------------------------------------
 namespace fast {
 
-constexpr int kT = 512;
+#ifndef SFA_FFT_THREADS
+#define SFA_FFT_THREADS 512
+#endif
+constexpr int kT = SFA_FFT_THREADS;
 __host__ __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
 __host__ __device__ __forceinline__ int seq_stride(int m) { return m + (m >> 4) + 2; }
 
@@ -369,23 +372,29 @@ __device__ __forceinline__ void pass(cf* data, int sstride, const cf* __restrict
             if (k) {
                 // twiddles w^(r k tstep), r = 1 .. R-1: the powers of two come from the table (their addresses
                 // r k tstep are far apart -- up to 16-way bank conflicts if all R-1 were loaded), the others
-                // are products of at most three of them (error ~2e-7, well below the FP32 transform's own)
-                cf wp[R];
+                // are products of at most three of them (error ~2e-7, well below the FP32 transform's own).
+                // Applied one after the other so that few of them are live at a time (64 registers per thread).
+                cf p2[4];                                       // w^1, w^2, w^4, w^8
 #pragma unroll
-                for (int r = 1; r < R; r <<= 1) {
-                    wp[r] = tw[r * k * tstep];
-                    if (kInv) wp[r].y = -wp[r].y;
-                }
-#pragma unroll
-                for (int r = 3; r < R; ++r) {
-                    if (r & (r - 1)) {                          // not a power of two: top bit times the rest
-                        int top = 1;
-                        while (top * 2 <= r) top *= 2;
-                        wp[r] = cmul(wp[top], wp[r - top]);
+                for (int b = 0; b < 4; ++b) {
+                    if ((1 << b) < R) {
+                        p2[b] = tw[(1 << b) * k * tstep];
+                        if (kInv) p2[b].y = -p2[b].y;
                     }
                 }
 #pragma unroll
-                for (int r = 1; r < R; ++r) v[r] = cmul(v[r], wp[r]);
+                for (int r = 1; r < R; ++r) {
+                    cf w = mk<float>(1.f, 0.f);
+                    bool first = true;
+#pragma unroll
+                    for (int b = 3; b >= 0; --b) {
+                        if (r & (1 << b)) {
+                            w = first ? p2[b] : cmul(w, p2[b]);
+                            first = false;
+                        }
+                    }
+                    v[r] = cmul(v[r], w);
+                }
             }
             dft_reg<R, kInv>(v);
         }
