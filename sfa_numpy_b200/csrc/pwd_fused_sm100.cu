@@ -353,13 +353,18 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 #pragma unroll
                         for (int ks = 0; ks < kMaxK / 8; ++ks) {
                             if (ks < prm.ksteps && !(prm.debug & 8)) {
+#ifdef SFA_DEBUG_HOOKS
+                                // timing probe (results are garbage): the hi*hi pass as a 16-bit-kind pass with half the
+                                // k-steps, i.e. the instruction stream an fp16-split variant would issue
+                                if ((prm.debug & 256) && pass == 0 && (ks & 1)) continue;
+#endif
                                 const int kb = ks >> 2, kk = ks & 3;
                                 const uint64_t b_re = bdesc + (uint64_t)((((bp + 0) * 2 + kb) * kBoxBytes + kk * 32) >> 4);
                                 const uint64_t b_im = bdesc + (uint64_t)((((bp + 1) * 2 + kb) * kBoxBytes + kk * 32) >> 4);
                                 const uint32_t a_re = a0 + (ap + 0) * kMaxK + ks * 8;
                                 const uint32_t a_im = a0 + (ap + 1) * kMaxK + ks * 8;
                                 const uint32_t accum = (pass == 0 && ks == 0) ? 0u : 1u;
-                                if (bf) {
+                                if (bf || ((prm.debug & 256) && pass == 0)) {
                                     umma_bf16_ts(d_re, a_re, b_re, idesc_bf, accum);
                                     umma_bf16_ts(d_re, a_im, b_im, idesc_bf_neg, 1u);
                                     umma_bf16_ts(d_im, a_re, b_im, idesc_bf, accum);
