@@ -211,14 +211,23 @@ def map_peer_buffers(local, group=None):
     fn, args = reduce_tensor(local)
     handles = [None] * world
     dist.all_gather_object(handles, (fn, args), group=group)
-    peers = []
-    for r in range(world):
-        if r == rank:
-            peers.append(local)
-        else:
-            f, a = handles[r]
-            peers.append(f(*a))
-    dist.barrier(group=group)                                  # nobody frees its buffer before all have opened it
+    peers, err = [], None
+    try:
+        for r in range(world):
+            if r == rank:
+                peers.append(local)
+            else:
+                f, a = handles[r]
+                peers.append(f(*a))
+    except Exception as e:                                     # e.g. no IPC / peer access between two of the devices
+        err = e
+    # all ranks agree on the outcome (a rank that raised alone would leave the others waiting in the next collective);
+    # the reduction also keeps every buffer alive until all ranks have opened it
+    ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=local.device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
+        raise RuntimeError("peer mapping of the output buffers failed on at least one rank" +
+                           (": %r" % (err,) if err is not None else ""))
     return peers
 
 
