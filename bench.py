@@ -42,8 +42,33 @@ _STDOUT_FD = os.dup(1)
 os.dup2(2, 1)
 
 
+_EMIT_LOCK = threading.Lock()
+_EMITTED = [False]
+
+
 def emit(line):
-    os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+    """Write THE JSON line (once: the watchdog and the normal path may race)."""
+    with _EMIT_LOCK:
+        if _EMITTED[0]:
+            return
+        _EMITTED[0] = True
+        os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+
+
+def start_watchdog(seconds, line, rank):
+    """Safety net for the sections after the headline measurement (multi-GPU variants, e2e, extra rows): if they
+    have not finished after `seconds`, rank 0 prints the line with what it has, and every rank leaves.  A hang in
+    an optional section must not cost the measured headline."""
+    def fire():
+        if rank == 0:
+            snap = dict(line)
+            snap["watchdog"] = "sections after the headline measurement did not finish within %d s; line emitted as is" % seconds
+            emit(snap)
+        os._exit(0 if rank == 0 else 0)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
 
 import numpy as np  # noqa: E402
 
@@ -715,6 +740,7 @@ def main():
             "bins_per_gpu": nb,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "parity_check": pcheck}
 
+    wd = start_watchdog(900, line, rank)      # everything below is explanation; the headline above is safe
     # ---- multi-GPU: the three readings of "sharded over the GPUs with an all-gather of the beam maps" ----
     if world > 1:
         try:
@@ -863,11 +889,21 @@ def main():
             for _ in range(3):
                 s12()
             torch.cuda.synchronize()
-            eager_us = timed(s12, n=20) * 1e3
+            def local_ms(fn, n):                     # rank-0-only section: no barriers in here
+                fn()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) / n
+            eager_us = local_ms(s12, 20) * 1e3
             g12 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g12):
                 s12()
-            graph_us = timed(lambda: g12.replay(), n=50) * 1e3
+            graph_us = local_ms(lambda: g12.replay(), 50) * 1e3
             evals = (Q + L) * (N + 1) ** 2 + F * (N + 1)
             line["stage12_graph"] = {"config": "cfg3: sht_matrix at 64 mics + 2562 look dirs, spherical_pw + regularize at 1024 bins",
                                      "eager_us": eager_us, "graph_us": graph_us, "evals": evals,
@@ -891,7 +927,9 @@ def main():
         emit(line)
     if world > 1:
         dist.barrier()                 # rank 0 may still be timing its CPU / single-GPU extras
+        wd.cancel()
         dist.destroy_process_group()
+    wd.cancel()
 
 
 def scaling_variants(torch, dist, sdist, S, bf, timed, world, rank, dev, args, cfg, step_ms, gather_maps, Xh, f0):
