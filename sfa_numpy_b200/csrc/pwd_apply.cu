@@ -35,9 +35,9 @@ size_t cgemm3x_kloop_scratch_bytes(long long K, int hybrid);
 bool pwd_fused_supported(long long L, long long Q, long long T, int Cd, long long out_ld, const void* out);
 size_t pwd_fused_g2_bytes(long long L, long long Q, int Cd);
 size_t pwd_fused_xs_bytes(long long nf, long long L, long long Q, long long T);
-int launch_group_products_g2(const double2* YL, const double2* YQt, long long L, long long Q, int M, int Cd,
+int launch_group_products_g2(const double2* YL, const double2* YQ, long long L, long long Q, int M, int Cd,
                              int per_order, float* G2, cudaStream_t st);
-int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd, const float* G2, const float2* d,
+int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd, const float* G2, const double2* d,
                      const float2* X, float* Xs, float2* out, long long ldo, float* power, int hybrid,
                      cudaStream_t st);
 
@@ -697,13 +697,8 @@ static int pwd_prepare(const sfa_pwd_shape* s, const Plan& p, const double2* yl,
     const int M = s->M, Cd = s->Cd;
     const bool c64 = is_c64(s);
     const long long LQ = L * p.Qp;
-    if (p.fused) {
-        double2* yqt = reinterpret_cast<double2*>(w + p.off_YQt);
-        conj_transpose_kernel<<<grid1d(Q * M), 256, 0, st>>>(yq, Q, M, yqt);
-        SFA_LAUNCH_CHECK();
-        return launch_group_products_g2(yl, yqt, L, Q, M, Cd, s->d_is_per_order,
-                                        reinterpret_cast<float*>(w + p.off_G2), st);
-    }
+    if (p.fused)
+        return launch_group_products_g2(yl, yq, L, Q, M, Cd, s->d_is_per_order, reinterpret_cast<float*>(w + p.off_G2), st);
     if (p.form == 1) {
         double2* yqt = reinterpret_cast<double2*>(w + p.off_YQt);
         conj_transpose_kernel<<<grid1d(Q * M), 256, 0, st>>>(yq, Q, M, yqt);
@@ -758,10 +753,7 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
         float2* o = reinterpret_cast<float2*>(out);
         if (p.fused) {
             if (((uintptr_t)out) & 15) return SFA_ERR_INVALID;              // (a null `out` = power map only)
-            float2* dF = reinterpret_cast<float2*>(w + p.off_dF);
-            d_to_float_kernel<<<grid1d(nf * Cd), 256, 0, st>>>(dd, nf * Cd, dF);
-            SFA_LAUNCH_CHECK();
-            return launch_pwd_fused(nf, L, Q, T, Cd, reinterpret_cast<const float*>(w + p.off_G2), dF, x,
+            return launch_pwd_fused(nf, L, Q, T, Cd, reinterpret_cast<const float*>(w + p.off_G2), dd, x,
                                     reinterpret_cast<float*>(w + p.off_Xs), o, p.Old, power, is_hybrid(s), st);
         }
         if (p.form == 1) {

@@ -116,6 +116,10 @@ __device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* map, const 
 constexpr int kStoreWarpBytes = kStoreRing * 2 * kStoreBoxBytes;
 
 
+__device__ __forceinline__ float2 ld_filter(const double2* p) {
+    const double2 v = __ldg(p);
+    return make_float2((float)v.x, (float)v.y);
+}
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -145,7 +149,7 @@ struct Params {
     int ngroups;                 // columns of d (<= NG; any number up to 64 for NG = 0)
     const float4* G2;            // [ltiles][ngroups][Kh][128] : (G[g][l][2j], G[g][l][2j+1]) per lane l
     int Kh;                      // ksteps * 4 column pairs
-    const float2* d;             // [F][ngroups] complex64
+    const double2* d;            // [F][ngroups] radial filters as the caller holds them (complex128), narrowed on load
     int ltiles, lt_groups, csize, t_tiles;
     long long groups;            // F * lt_groups
     float* power;                // nullable: [F][L] mean_t |q|^2, accumulated in the epilogue (a CTA owns whole rows)
@@ -457,7 +461,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 float2 dg[NGA];
 #pragma unroll
                 for (int g = 0; g < NGA; ++g)
-                    dg[g] = (g < prm.ngroups) ? __ldg(prm.d + f * prm.ngroups + g) : make_float2(0.f, 0.f);
+                    dg[g] = (g < prm.ngroups) ? ld_filter(prm.d + f * prm.ngroups + g) : make_float2(0.f, 0.f);
 #pragma unroll
                 for (int g = 0; g < NGA; ++g)
                     if (g < prm.ngroups && !(prm.debug & 2)) add_group(dg[g], gp + (size_t)g * prm.Kh * kTileL);
@@ -465,7 +469,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 // many groups (circular arrays: one per column, up to 64): plain loop
 #pragma unroll 1
                 for (int g = 0; g < prm.ngroups; ++g)
-                    add_group(__ldg(prm.d + f * prm.ngroups + g), gp + (size_t)g * prm.Kh * kTileL);
+                    add_group(ld_filter(prm.d + f * prm.ngroups + g), gp + (size_t)g * prm.Kh * kTileL);
             }
             // the MMAs of the previous task must have finished reading the operand columns
             mbar_wait(&bars->a_empty, a_phase ^ 1);
@@ -645,7 +649,7 @@ __device__ __forceinline__ void convert_slice(const Params& prm, unsigned char* 
             const int r = i / prm.Kh, j = i - r * prm.Kh;
             float ar0 = 0.f, ai0 = 0.f, ar1 = 0.f, ai1 = 0.f;
             for (int g = 0; g < prm.ngroups; ++g) {
-                const float2 dg = __ldg(prm.d + fc * prm.ngroups + g);
+                const float2 dg = ld_filter(prm.d + fc * prm.ngroups + g);
                 const float4 v = __ldg(prm.G2_last + ((size_t)g * prm.Kh + j) * kTileL + r);
                 ar0 = fmaf(dg.x, v.x, ar0);
                 ar0 = fmaf(-dg.y, v.y, ar0);
@@ -780,7 +784,7 @@ __device__ void convert_ahead(const Params& prm, Barriers* bars, unsigned char* 
 constexpr int kSplitT = 32;                          // frames per tile of the pre-pass
 __global__ void __launch_bounds__(256)
 x_split_tail_kernel(const float2* __restrict__ X, int Q, long long T, int Kp, int hybrid, float* __restrict__ Xs,
-                    const float4* __restrict__ G2_last, int ngroups, int Kh, const float2* __restrict__ d,
+                    const float4* __restrict__ G2_last, int ngroups, int Kh, const double2* __restrict__ d,
                     float2* __restrict__ out, long long L, long long Lm, int rem, long long ldo,
                     float* __restrict__ power) {
     __shared__ float2 tile[kMaxK][kSplitT + 1];
@@ -793,7 +797,7 @@ x_split_tail_kernel(const float2* __restrict__ X, int Q, long long T, int Kp, in
             const int r = i / Kh, j = i - r * Kh;
             float ar0 = 0.f, ai0 = 0.f, ar1 = 0.f, ai1 = 0.f;
             for (int g = 0; g < ngroups; ++g) {
-                const float2 dg = __ldg(d + f * ngroups + g);
+                const float2 dg = ld_filter(d + f * ngroups + g);
                 const float4 v = __ldg(G2_last + ((size_t)g * Kh + j) * kTileL + r);
                 ar0 = fmaf(dg.x, v.x, ar0);
                 ar0 = fmaf(-dg.y, v.y, ar0);
@@ -887,37 +891,43 @@ __device__ __forceinline__ int order_of_col(int i) {     // radial.repeat_n_m: c
 
 // Group products in the builders' layout (FP64 accumulate, stored as float):
 //   G2[lt][g][j][lane] = (G_g[l][2j], G_g[l][2j+1]),  l = lt*128 + lane,  G_g[l][q] = sum_{m in g} Y_L[l,m] conj(Y_Q[q,m])
-// YQt = conj(Y_Q)^T [M][Q].  Rows l >= L and columns q >= Q are zero.
-__global__ void group_products_g2_kernel(const double2* __restrict__ YL, const double2* __restrict__ YQt, long long L,
-                                         int Q, int M, int G, int per_order, int Kh, long long total,
-                                         float4* __restrict__ out) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int lane = (int)(i & (kTileL - 1));
-        long long r = i >> 7;
-        const int j = (int)(r % Kh);
-        r /= Kh;
-        const int g = (int)(r % G);
-        const long long lt = r / G;
-        const long long l = lt * kTileL + lane;
-        double s[4] = {0.0, 0.0, 0.0, 0.0};
+// Rows l >= L and columns q >= Q are zero.  One block per (l-tile, group), one thread per row: the thread's
+// Y_L[l, m0..m1) stays in L1 over the 32 column pairs, conj(Y_Q[q, m]) is the same address for the whole warp,
+// and every store is 16 contiguous bytes per lane (2 KB per block and column pair); blockIdx.y splits the column
+// pairs so that the grid fills the machine.  Reads Y_Q as it is (no conjugate-transposed copy).
+__global__ void __launch_bounds__(kTileL)
+group_products_g2_kernel(const double2* __restrict__ YL, const double2* __restrict__ YQ, long long L, int Q, int M,
+                         int G, int per_order, int Kh, float4* __restrict__ out) {
+    const int lane = threadIdx.x;
+    const long long lt = blockIdx.x / G;
+    const int g = (int)(blockIdx.x - lt * G);
+    const long long l = lt * kTileL + lane;
+    const int m0 = per_order ? g * g : g;
+    int m1 = per_order ? (g + 1) * (g + 1) : g + 1;
+    if (m1 > M) m1 = M;
+    float4* o = out + ((size_t)(lt * G + g) * Kh) * kTileL + lane;
+    const double2* arow = YL + l * M;
+    const int jper = (Kh + gridDim.y - 1) / gridDim.y;       // column pairs per block (blockIdx.y splits them)
+    const int j0 = blockIdx.y * jper, j1 = (j0 + jper < Kh) ? j0 + jper : Kh;
+    for (int j = j0; j < j1; ++j) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         if (l < L) {
-            const int m0 = per_order ? g * g : g;
-            const int m1 = per_order ? (g + 1) * (g + 1) : g + 1;
-            for (int m = m0; m < m1 && m < M; ++m) {
-                const double2 a = YL[l * M + m];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int q = 2 * j + e;
-                    if (q < Q) {
-                        const double2 b = YQt[(long long)m * Q + q];
-                        s[2 * e] += a.x * b.x - a.y * b.y;
-                        s[2 * e + 1] += a.y * b.x + a.x * b.y;
-                    }
+            const int q0 = 2 * j, q1 = 2 * j + 1;
+            for (int m = m0; m < m1; ++m) {
+                const double2 a = arow[m];
+                if (q0 < Q) {
+                    const double2 b = YQ[(long long)q0 * M + m];                 // conj(b) = (b.x, -b.y)
+                    s0 += a.x * b.x + a.y * b.y;
+                    s1 += a.y * b.x - a.x * b.y;
+                }
+                if (q1 < Q) {
+                    const double2 b = YQ[(long long)q1 * M + m];
+                    s2 += a.x * b.x + a.y * b.y;
+                    s3 += a.y * b.x - a.x * b.y;
                 }
             }
         }
-        out[i] = make_float4((float)s[0], (float)s[1], (float)s[2], (float)s[3]);
+        o[(size_t)j * kTileL] = make_float4((float)s0, (float)s1, (float)s2, (float)s3);
     }
 }
 
@@ -948,22 +958,22 @@ size_t pwd_fused_xs_bytes(long long nf, long long L, long long Q, long long T) {
            (size_t)nf * max_slices * fused::kTailMaxRows * sizeof(float);
 }
 
-int launch_group_products_g2(const double2* YL, const double2* YQt, long long L, long long Q, int M, int Cd,
+int launch_group_products_g2(const double2* YL, const double2* YQ, long long L, long long Q, int M, int Cd,
                              int per_order, float* G2, cudaStream_t st) {
     const long long ltiles = ceil_div(L, fused::kTileL);
     const int Kh = (int)ceil_div(Q, 8) * 4;
-    const long long total = ltiles * Cd * Kh * fused::kTileL;
-    long long blocks = ceil_div(total, 256);
-    const long long cap = (long long)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    fused::group_products_g2_kernel<<<(unsigned)blocks, 256, 0, st>>>(YL, YQt, L, (int)Q, M, Cd, per_order, Kh, total,
-                                                                      reinterpret_cast<float4*>(G2));
+    // about eight blocks per SM
+    long long ysplit = ceil_div((long long)sm_count() * 8, ltiles * Cd);
+    if (ysplit > Kh) ysplit = Kh;
+    if (ysplit < 1) ysplit = 1;
+    fused::group_products_g2_kernel<<<dim3((unsigned)(ltiles * Cd), (unsigned)ysplit), fused::kTileL, 0, st>>>(
+        YL, YQ, L, (int)Q, M, Cd, per_order, Kh, reinterpret_cast<float4*>(G2));
     SFA_LAUNCH_CHECK();
     return SFA_OK;
 }
 
-// q[f] = (sum_g d[f][g] G_g) X[f] for nf bins.  d: complex64 [nf][Cd]; X: [nf][Q][T]; out: [nf][L][ldo].
-int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd, const float* G2, const float2* d,
+// q[f] = (sum_g d[f][g] G_g) X[f] for nf bins.  d: complex128 [nf][Cd]; X: [nf][Q][T]; out: [nf][L][ldo].
+int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd, const float* G2, const double2* d,
                      const float2* X, float* Xs, float2* out, long long ldo, float* power, int hybrid,
                      cudaStream_t st) {
     using namespace fused;
