@@ -297,7 +297,14 @@ namespace fast {
 #ifndef SFA_FFT_THREADS
 #define SFA_FFT_THREADS 512
 #endif
+#ifndef SFA_FFT_PAIRS
+#define SFA_FFT_PAIRS 8
+#endif
+#ifndef SFA_FFT_CTAS
+#define SFA_FFT_CTAS 1
+#endif
 constexpr int kT = SFA_FFT_THREADS;
+constexpr int kCtasPerSm = SFA_FFT_CTAS;
 __host__ __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
 __host__ __device__ __forceinline__ int seq_stride(int m) { return m + (m >> 4) + 2; }
 
@@ -352,56 +359,74 @@ __device__ __forceinline__ void dft_reg(cf (&v)[R]) {
 }
 
 // One Stockham pass of radix R over `nseq` sequences of length m (in place, see above).  Ns = product of the
-// radices of the earlier passes.  blockDim.x = kT, m / R <= kT.  Ends with a barrier.
-template <int R, bool kInv>
-__device__ __forceinline__ void pass(cf* data, int sstride, const cf* __restrict__ tw, int m, int Ns, int nseq) {
+// radices of the earlier passes (compile time).  blockDim.x = kT, 16 <= m / R <= kT.  Ends with a barrier.
+// All 2 R shared-memory accesses of a butterfly are base + r * stride with strides that do not depend on the
+// thread: inputs j + r m/R sit at pad(j) + r (m/R + m/(16 R)), outputs j0 + c Ns at pad(j0) + c (Ns + Ns/16)
+// (Ns = 1: the 16 outputs of the first pass are adjacent) -- no per-access padding arithmetic.
+template <int R, bool kInv, int Ns>
+__device__ __forceinline__ void pass(cf* data, int sstride, const cf* __restrict__ tw, int m, int nseq) {
     const int per_seq = m / R;
     const int G = kT / per_seq;                                 // sequences per round
-    const int s_in = threadIdx.x / per_seq, j = threadIdx.x - s_in * per_seq;
+    const int lps = 31 - __clz(per_seq);                        // per_seq is a power of two
+    const int s_in = (int)threadIdx.x >> lps, j = (int)threadIdx.x & (per_seq - 1);
     const int k = j & (Ns - 1);
     const int tstep = m / (Ns * R);
     const int j0 = (j - k) * R + k;
+    const int rbase = pad_idx(j), rstride = per_seq + (per_seq >> 4);
+    const int wbase = pad_idx(j0);
+    constexpr int wstride = Ns >= 16 ? Ns + Ns / 16 : Ns;
     for (int s0 = 0; s0 < nseq; s0 += G) {
         const int s = s0 + s_in;
         const bool act = s < nseq;
         cf v[R];
-        cf* a = data + (size_t)s * sstride;
+        cf* const a = data + s * sstride;
         if (act) {
+            const cf* rd = a + rbase;
 #pragma unroll
-            for (int r = 0; r < R; ++r) v[r] = a[pad_idx(j + r * per_seq)];
-            if (k) {
+            for (int r = 0; r < R; ++r) v[r] = rd[r * rstride];
+            if (Ns > 1 && k) {
                 // twiddles w^(r k tstep), r = 1 .. R-1: the powers of two come from the table (their addresses
                 // r k tstep are far apart -- up to 16-way bank conflicts if all R-1 were loaded), the others
-                // are products of at most three of them (error ~2e-7, well below the FP32 transform's own).
-                // Applied one after the other so that few of them are live at a time (64 registers per thread).
-                cf p2[4];                                       // w^1, w^2, w^4, w^8
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    if ((1 << b) < R) {
-                        p2[b] = tw[(1 << b) * k * tstep];
-                        if (kInv) p2[b].y = -p2[b].y;
-                    }
-                }
-#pragma unroll
-                for (int r = 1; r < R; ++r) {
-                    cf w = mk<float>(1.f, 0.f);
-                    bool first = true;
-#pragma unroll
-                    for (int b = 3; b >= 0; --b) {
-                        if (r & (1 << b)) {
-                            w = first ? p2[b] : cmul(w, p2[b]);
-                            first = false;
+                // are products of them (error ~2e-7, well below the FP32 transform's own)
+                cf w1 = tw[k * tstep];
+                if (kInv) w1.y = -w1.y;
+                v[1] = cmul(v[1], w1);
+                if (R > 2) {
+                    cf w2 = tw[2 * k * tstep];
+                    if (kInv) w2.y = -w2.y;
+                    const cf w3 = cmul(w2, w1);
+                    v[2] = cmul(v[2], w2);
+                    v[3] = cmul(v[3], w3);
+                    if (R > 4) {
+                        cf w4 = tw[4 * k * tstep];
+                        if (kInv) w4.y = -w4.y;
+                        v[4] = cmul(v[4], w4);
+                        v[5] = cmul(v[5], cmul(w4, w1));
+                        v[6] = cmul(v[6], cmul(w4, w2));
+                        v[7] = cmul(v[7], cmul(w4, w3));
+                        if (R > 8) {
+                            cf w8 = tw[8 * k * tstep];
+                            if (kInv) w8.y = -w8.y;
+                            const cf w12 = cmul(w8, w4);
+                            v[8 % R] = cmul(v[8 % R], w8);
+                            v[9 % R] = cmul(v[9 % R], cmul(w8, w1));
+                            v[10 % R] = cmul(v[10 % R], cmul(w8, w2));
+                            v[11 % R] = cmul(v[11 % R], cmul(w8, w3));
+                            v[12 % R] = cmul(v[12 % R], w12);
+                            v[13 % R] = cmul(v[13 % R], cmul(w12, w1));
+                            v[14 % R] = cmul(v[14 % R], cmul(w12, w2));
+                            v[15 % R] = cmul(v[15 % R], cmul(w12, w3));
                         }
                     }
-                    v[r] = cmul(v[r], w);
                 }
             }
             dft_reg<R, kInv>(v);
         }
         __syncthreads();                                        // every butterfly of the round has its inputs
         if (act) {
+            cf* wr = a + wbase;
 #pragma unroll
-            for (int r = 0; r < R; ++r) a[pad_idx(j0 + brev<R>(r) * Ns)] = v[r];
+            for (int r = 0; r < R; ++r) wr[brev<R>(r) * wstride] = v[r];
         }
     }
     __syncthreads();
@@ -410,18 +435,18 @@ __device__ __forceinline__ void pass(cf* data, int sstride, const cf* __restrict
 // all passes for length m = 2^log2m (8 <= log2m <= 12): 16 x 16 x {1, 2, 4, 8, 16}
 template <bool kInv>
 __device__ __forceinline__ void fft_inplace(cf* data, int sstride, const cf* tw, int m, int log2m, int nseq) {
-    pass<16, kInv>(data, sstride, tw, m, 1, nseq);
-    pass<16, kInv>(data, sstride, tw, m, 16, nseq);
+    pass<16, kInv, 1>(data, sstride, tw, m, nseq);
+    pass<16, kInv, 16>(data, sstride, tw, m, nseq);
     switch (log2m) {
-        case 9: pass<2, kInv>(data, sstride, tw, m, 256, nseq); break;
-        case 10: pass<4, kInv>(data, sstride, tw, m, 256, nseq); break;
-        case 11: pass<8, kInv>(data, sstride, tw, m, 256, nseq); break;
-        case 12: pass<16, kInv>(data, sstride, tw, m, 256, nseq); break;
+        case 9: pass<2, kInv, 256>(data, sstride, tw, m, nseq); break;
+        case 10: pass<4, kInv, 256>(data, sstride, tw, m, nseq); break;
+        case 11: pass<8, kInv, 256>(data, sstride, tw, m, nseq); break;
+        case 12: pass<16, kInv, 256>(data, sstride, tw, m, nseq); break;
         default: break;
     }
 }
 
-__global__ void __launch_bounds__(kT, 1)
+__global__ void __launch_bounds__(kT, kCtasPerSm)
 irfft_fast_kernel(const IrfftParams prm, const cf* __restrict__ q, float* __restrict__ out, const cf* __restrict__ tw_g) {
     extern __shared__ unsigned char smem_raw[];
     const int m = prm.m, nseq = prm.nseq;                        // nseq is a power of two
@@ -507,7 +532,7 @@ irfft_fast_kernel(const IrfftParams prm, const cf* __restrict__ q, float* __rest
     }
 }
 
-__global__ void __launch_bounds__(kT, 1)
+__global__ void __launch_bounds__(kT, kCtasPerSm)
 stft_fast_kernel(const StftParams prm, const float* __restrict__ x, const float* __restrict__ win, cf* __restrict__ X,
                  const cf* __restrict__ tw_g) {
     extern __shared__ unsigned char smem_raw[];
@@ -552,7 +577,7 @@ stft_fast_kernel(const StftParams prm, const float* __restrict__ x, const float*
 }
 
 static inline bool supported(long long m) { return m >= 256 && m <= 4096 && (m & (m - 1)) == 0; }
-static inline int pairs_per_tile(long long m) { return m <= 2048 ? 8 : 4; }
+static inline int pairs_per_tile(long long m) { return m <= 2048 ? SFA_FFT_PAIRS : SFA_FFT_PAIRS / 2; }
 static inline size_t smem_bytes(long long m, int nseq) { return ((size_t)m + (size_t)nseq * seq_stride((int)m)) * sizeof(cf); }
 
 }  // namespace fast
@@ -600,7 +625,7 @@ static int run_irfft(long long F, long long C, long long n, const void* q, long 
         const size_t smem = fast::smem_bytes(m, (int)nseq);
         SFA_ENSURE_DYN_SMEM(fast::irfft_fast_kernel, smem);
         long long blocks = ceil_div(C, 2 * nseq);
-        if (blocks > sm_count()) blocks = sm_count();
+        if (blocks > (long long)sm_count() * fast::kCtasPerSm) blocks = (long long)sm_count() * fast::kCtasPerSm;
         prof_begin(st);
         fast::irfft_fast_kernel<<<(unsigned)blocks, fast::kT, smem, st>>>(prm, reinterpret_cast<const fast::cf*>(q),
                                                                           reinterpret_cast<float*>(out),
@@ -665,7 +690,7 @@ static int run_stft(long long Q, long long S, int nfft, int hop, long long Fk, c
         const size_t smem = fast::smem_bytes(nfft, (int)nseq);
         SFA_ENSURE_DYN_SMEM(fast::stft_fast_kernel, smem);
         long long blocks = Q * ceil_div(T, 2 * nseq);
-        if (blocks > sm_count()) blocks = sm_count();
+        if (blocks > (long long)sm_count() * fast::kCtasPerSm) blocks = (long long)sm_count() * fast::kCtasPerSm;
         fast::stft_fast_kernel<<<(unsigned)blocks, fast::kT, smem, st>>>(prm, reinterpret_cast<const float*>(x),
                                                                          reinterpret_cast<const float*>(win),
                                                                          reinterpret_cast<fast::cf*>(X),
