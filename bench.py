@@ -852,7 +852,7 @@ def main():
                 dtp = float(tdp.item())
                 e2e["e2e_power_map"] = {"value": F * L * T / dtp, "unit": "outputs/s", "ms_per_step": dtp * 1e3,
                                         "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": 4 * F * L,
-                                        "api": "sfa_pwd_host_run_power: spectra in, beam power maps out; the beams stay on the device"}
+                                        "api": "sfa_pwd_host_run_power: spectra in, beam power maps out; map-only kernel runs (the beams are never written), H2D-bound"}
             except Exception as e:
                 e2e["e2e_power_map"] = {"error": repr(e)}
             line["e2e"] = e2e

@@ -1074,9 +1074,11 @@ extern "C" int sfa_pwd_host_run_power(sfa_pwd_host_ctx* c, const void* X_host, v
         for (long long g0 = 0; g0 < nf; g0 += c->plan.fc) {
             const long long ng = (nf - g0 < c->plan.fc) ? (nf - g0) : c->plan.fc;
             float* pw = power_host ? c->d_P + (f0 + g0) * s->L : nullptr;
+            // only the map is wanted and the plan is the fused kernel: the beams never leave tensor memory
+            const bool map_only = !out_host && pw && c->plan.fused;
             int rc = pwd_run_bins(s, c->plan, ng, reinterpret_cast<const double2*>(c->d_YL),
                                   reinterpret_cast<const double2*>(c->d_d) + (f0 + g0) * s->Cd,
-                                  c->d_X[slot] + g0 * x_bin, c->d_O[slot] + g0 * o_bin_dev, w, c->s_cmp,
+                                  c->d_X[slot] + g0 * x_bin, map_only ? nullptr : c->d_O[slot] + g0 * o_bin_dev, w, c->s_cmp,
                                   c->plan.fused ? pw : nullptr);
             if (rc != SFA_OK) return rc;
             if (pw && !c->plan.fused) {

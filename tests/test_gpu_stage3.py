@@ -252,6 +252,15 @@ def _host_path_case(S, T, N=4, grid=None):
         assert bin_err(q, ref) < tol
         q2 = host(X)                     # pageable memory works too
         assert np.array_equal(q, q2)
+        if precision != "c128":
+            # power maps through the host path: with the beams, and alone (fused plans: map-only kernel runs)
+            pm_ref = np.mean(np.abs(ref) ** 2, axis=2)
+            q3 = np.empty_like(q)
+            pm_a = host.power_map(Xp, out=q3)
+            pm_b = host.power_map(Xp)
+            assert np.array_equal(q3, q)
+            for pm in (pm_a, pm_b):
+                assert np.max(np.abs(pm - pm_ref) / np.max(pm_ref, axis=1, keepdims=True)) < 1e-5
         host.close()
 
 
