@@ -61,10 +61,17 @@ def start_watchdog(seconds, line, rank):
     an optional section must not cost the measured headline."""
     def fire():
         if rank == 0:
-            snap = dict(line)
-            snap["watchdog"] = "sections after the headline measurement did not finish within %d s; line emitted as is" % seconds
+            for _ in range(5):                       # the main thread may be adding a key right now
+                try:
+                    snap = dict(line)
+                    snap["watchdog"] = ("sections after the headline measurement did not finish within %d s; "
+                                        "line emitted as is" % seconds)
+                    json.dumps(snap)
+                    break
+                except Exception:
+                    time.sleep(0.05)
             emit(snap)
-        os._exit(0 if rank == 0 else 0)
+        os._exit(0)
     t = threading.Timer(seconds, fire)
     t.daemon = True
     t.start()
