@@ -898,6 +898,7 @@ __device__ __forceinline__ int order_of_col(int i) {     // radial.repeat_n_m: c
 __global__ void __launch_bounds__(kTileL)
 group_products_g2_kernel(const double2* __restrict__ YL, const double2* __restrict__ YQ, long long L, int Q, int M,
                          int G, int per_order, int Kh, float4* __restrict__ out) {
+    extern __shared__ double2 sq[];                              // conj-free copy of Y_Q[q0 .. q1)[m0 .. m1): [q][nm]
     const int lane = threadIdx.x;
     const long long lt = blockIdx.x / G;
     const int g = (int)(blockIdx.x - lt * G);
@@ -905,26 +906,30 @@ group_products_g2_kernel(const double2* __restrict__ YL, const double2* __restri
     const int m0 = per_order ? g * g : g;
     int m1 = per_order ? (g + 1) * (g + 1) : g + 1;
     if (m1 > M) m1 = M;
+    const int nm = m1 - m0;
     float4* o = out + ((size_t)(lt * G + g) * Kh) * kTileL + lane;
-    const double2* arow = YL + l * M;
     const int jper = (Kh + gridDim.y - 1) / gridDim.y;       // column pairs per block (blockIdx.y splits them)
     const int j0 = blockIdx.y * jper, j1 = (j0 + jper < Kh) ? j0 + jper : Kh;
+    const int nq = 2 * (j1 - j0);
+    for (int i = lane; i < nq * nm; i += kTileL) {
+        const int qq = i / nm, mm = i - qq * nm;
+        const int q = 2 * j0 + qq;
+        sq[i] = (q < Q) ? YQ[(long long)q * M + m0 + mm] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
     for (int j = j0; j < j1; ++j) {
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         if (l < L) {
-            const int q0 = 2 * j, q1 = 2 * j + 1;
-            for (int m = m0; m < m1; ++m) {
+            const double2* arow = YL + l * M + m0;
+            const double2* b0 = sq + (size_t)(2 * (j - j0)) * nm;
+            const double2* b1 = b0 + nm;
+            for (int m = 0; m < nm; ++m) {
                 const double2 a = arow[m];
-                if (q0 < Q) {
-                    const double2 b = YQ[(long long)q0 * M + m];                 // conj(b) = (b.x, -b.y)
-                    s0 += a.x * b.x + a.y * b.y;
-                    s1 += a.y * b.x - a.x * b.y;
-                }
-                if (q1 < Q) {
-                    const double2 b = YQ[(long long)q1 * M + m];
-                    s2 += a.x * b.x + a.y * b.y;
-                    s3 += a.y * b.x - a.x * b.y;
-                }
+                const double2 x = b0[m], y = b1[m];              // conj(x) = (x.x, -x.y)
+                s0 += a.x * x.x + a.y * x.y;
+                s1 += a.y * x.x - a.x * x.y;
+                s2 += a.x * y.x + a.y * y.y;
+                s3 += a.y * y.x - a.x * y.y;
             }
         }
         o[(size_t)j * kTileL] = make_float4((float)s0, (float)s1, (float)s2, (float)s3);
@@ -966,7 +971,11 @@ int launch_group_products_g2(const double2* YL, const double2* YQ, long long L, 
     long long ysplit = ceil_div((long long)sm_count() * 8, ltiles * Cd);
     if (ysplit > Kh) ysplit = Kh;
     if (ysplit < 1) ysplit = 1;
-    fused::group_products_g2_kernel<<<dim3((unsigned)(ltiles * Cd), (unsigned)ysplit), fused::kTileL, 0, st>>>(
+    const long long jper = ceil_div(Kh, ysplit);
+    const int nm_max = per_order ? 2 * Cd - 1 : 1;           // the largest group: order Cd - 1 has 2 Cd - 1 columns
+    const size_t smem = (size_t)2 * jper * nm_max * sizeof(double2);
+    if (smem > 48 * 1024) return SFA_ERR_UNSUPPORTED;
+    fused::group_products_g2_kernel<<<dim3((unsigned)(ltiles * Cd), (unsigned)ysplit), fused::kTileL, smem, st>>>(
         YL, YQ, L, (int)Q, M, Cd, per_order, Kh, reinterpret_cast<float4*>(G2));
     SFA_LAUNCH_CHECK();
     return SFA_OK;
