@@ -68,7 +68,7 @@ int sfa_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* Library-wide tuning knobs (process-global, initialised once at load time from the SFA_<KEY> environment
  * variables; no launch path calls getenv).  Keys: "pwd_chunk_mb" (scratch budget per frequency slab),
- * "no_fused", "fused_prepass", "fft_generic", "no_dmma", "no_kloop", "no_cluster", "no_fold", "no_tma_store", "old_build" (0/1: switch a kernel
+ * "no_fused", "no_legendre", "fused_prepass", "fft_generic", "no_dmma", "no_kloop", "no_cluster", "no_fold", "no_tma_store", "old_build" (0/1: switch a kernel
  * variant off -- test and tuning use), "kloop_block", "issuers", "fused_D", "fused_ring" (0 = automatic),
  * "reserve_sms" (SMs the persistent kernels leave free, e.g. for NCCL copy kernels running under them).  Unknown key: SFA_ERR_INVALID / NaN. */
 int sfa_set_option(const char* key, double value);
@@ -177,6 +177,10 @@ typedef struct {
     int64_t out_ld;        /* row pitch of `out` in elements (0 = T, i.e. contiguous [F, L, T]).  A pitch that
                               is a multiple of 32 frames (256 B) is worth ~1.4x of HBM write bandwidth: every
                               128-byte line of a row tile then belongs to one CTA                            */
+    int out_pad_writable;  /* nonzero: the caller owns the row padding of `out` (out_ld >= T rounded up to 16) and
+                              the kernels may overwrite the frames [T, roundup(T, 16)) of every row with zeros, so
+                              that every row ends on a whole 128-byte line (a partial line at each row end costs the
+                              store stream 15-20 % of its HBM bandwidth).  0: nothing beyond frame T is touched    */
 } sfa_pwd_shape;
 
 size_t sfa_pwd_work_bytes(const sfa_pwd_shape* s);

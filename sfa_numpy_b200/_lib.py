@@ -21,7 +21,7 @@ class PwdShape(ctypes.Structure):
     """sfa_pwd_shape of include/sfa_b200.h."""
     _fields_ = [("F", c_int64), ("L", c_int64), ("Q", c_int64), ("T", c_int64),
                 ("M", c_int), ("Cd", c_int), ("d_is_per_order", c_int),
-                ("precision", c_int), ("form", c_int), ("out_ld", c_int64)]
+                ("precision", c_int), ("form", c_int), ("out_ld", c_int64), ("out_pad_writable", c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/sfa_b200.h

@@ -534,7 +534,9 @@ int launch_cgemm3x(long long B, long long Nn, long long Mm, int K, const float* 
     // Only for single-pass products: the split-K accumulate passes rely on the TMA reduce-add store,
     // which needs whole tiles inside one batch (measured: folding + register read-modify-write is slower).
     const int fold = (p_shared && Mm <= 64 && B > 1 && out_mode == OUT_C64 && !options().no_fold) ? 1 : 0;
-    const int tma_store = (!fold && (ldo & 1) == 0 && (strideO & 1) == 0 && (((uintptr_t)out) & 15) == 0 &&
+    // (a TMA store clips a box in 16-byte units: with an odd number of frames per row -- 8 Mm bytes -- it would also
+    // write the element behind the row end, which belongs to the caller when the rows are padded)
+    const int tma_store = (!fold && (ldo & 1) == 0 && (Mm & 1) == 0 && (strideO & 1) == 0 && (((uintptr_t)out) & 15) == 0 &&
                            !options().no_tma_store) ? 1 : 0;
     CUtensorMap omap = map;
     if (tma_store) {

@@ -39,7 +39,7 @@ int launch_group_products_g2(const double2* YL, const double2* YQ, long long L, 
                              int per_order, float* G2, cudaStream_t st);
 int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd, const float* G2, const double2* d,
                      const float2* X, float* Xs, float2* out, long long ldo, float* power, int hybrid,
-                     cudaStream_t st);
+                     cudaStream_t st, int pad_writable);
 
 static inline bool use_kloop(long long K, int p_shared) { return K > 64 && p_shared && !options().no_kloop; }
 
@@ -600,7 +600,9 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
             // few frames (cfg 2: 33 groups, T = 256) that stream, not the MMAs, sets the pace (measured 0.60 ms
             // against 0.31 ms for the factored form)
             const double build_fma = rows * p->Qp * s->Cd * 8.0 / 30e12;
-            const double build_l2 = rows * p->Qp * s->Cd * 8.0 / 2.5e12;
+            // (spherical-harmonic operators with per-order filters are built by the Legendre recurrence: no stream)
+            const bool leg = s->d_is_per_order && s->Cd >= 2 && s->Cd <= 16;
+            const double build_l2 = leg ? 0.0 : rows * p->Qp * s->Cd * 8.0 / 2.5e12;
             const double build = build_fma > build_l2 ? build_fma : build_l2;
             const double bytes = (double)s->L * s->T * 8.0 / 4.5e12;
             const double t = (mma > bytes ? mma : bytes);
@@ -754,7 +756,8 @@ static int pwd_run_bins(const sfa_pwd_shape* s, const Plan& p, long long nf, con
         if (p.fused) {
             if (((uintptr_t)out) & 15) return SFA_ERR_INVALID;              // (a null `out` = power map only)
             return launch_pwd_fused(nf, L, Q, T, Cd, reinterpret_cast<const float*>(w + p.off_G2), dd, x,
-                                    reinterpret_cast<float*>(w + p.off_Xs), o, p.Old, power, is_hybrid(s), st);
+                                    reinterpret_cast<float*>(w + p.off_Xs), o, p.Old, power, is_hybrid(s), st,
+                                    s->out_pad_writable);
         }
         if (p.form == 1) {
             const float2* G = reinterpret_cast<const float2*>(w + p.off_G);
@@ -962,6 +965,7 @@ extern "C" int sfa_pwd_host_create(sfa_pwd_host_ctx** out_ctx, const sfa_pwd_sha
     sfa_pwd_host_ctx* c = new sfa_pwd_host_ctx();
     c->shape = *s;
     c->shape.out_ld = (s->T > 128) ? round_up(s->T, 32) : s->T;     // device-side row pitch of the beams
+    c->shape.out_pad_writable = 1;                                  // the device slabs are the library's own
     s = &c->shape;
     int rc = make_plan(s, &c->plan);
     if (rc != SFA_OK) {

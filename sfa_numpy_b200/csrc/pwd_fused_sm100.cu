@@ -133,6 +133,20 @@ __device__ __forceinline__ void st_f32_hint(float* p, float v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
 }
 
+// Addition-theorem build.  When Y_L and Y_Q are spherical-harmonic matrices (angular.sht_matrix; Y_Q may carry real
+// or complex quadrature weights) and the filters are per order, the group products collapse to
+//     G_n[l, q] = sum_m Y_n^m(l) conj(Y_n^m(q)) w_q = s_q (2n + 1) P_n(x_lq),    s_q = G_0[., q],  x_lq = cos angle(l, q)
+// so the steering tile is  A_f[l, q] = s_q sum_n (2n + 1) d_f[n] P_n(x_lq):  the builders run the three-term Legendre
+// recurrence on ONE float per entry instead of reading NG complex group products per entry -- 32 KB instead of 590 KB
+// per task out of L2 on the headline shape (13 GB per step; with the beam stores in flight that stream, not the
+// tensor pipe, set the pace of the kernel: 6.2 ms with it, 4.2 ms with the build switched off, tools/pad_ab.py).
+// Nothing is assumed: the preparation kernel computes s, x and the model in FP64 from the given matrices and
+// records the largest deviation of every G_n from it next to the largest |G_n|; the builders take this path only
+// if every group agrees to 1e-8 (relative to its largest entry), otherwise they read the table as before.
+constexpr int kLegMaxGroups = 16;
+constexpr size_t kLegHdrBytes = 128 * sizeof(unsigned) + 64 * sizeof(float2);      // devmag | s_q ; then xt
+constexpr float kLegTol = 1e-8f;
+
 constexpr int kConvT = 32;                           // frames per conversion tile
 constexpr int kConvSmemBytes = kMaxK * (kConvT + 1) * 8 + kTailMaxRows * kMaxK * 8 + kTailMaxRows * 4;
 struct Params;
@@ -155,6 +169,10 @@ struct Params {
     float* power;                // nullable: [F][L] mean_t |q|^2, accumulated in the epilogue (a CTA owns whole rows)
     int store_evict_first;       // beam stores with the L2 evict_first policy (output much larger than L2)
     int no_store;                // power map only: the beams are not written (out == nullptr)
+    long long Tst;               // frames per row covered by the store tensor map (T, or T - 1: see odd_last)
+    int odd_last;                // odd T without writable row padding: the tensor map ends at frame T - 1 (a TMA store
+                                 // clips a box in 16-byte units, so a map of 2 T floats would also write frame T) and
+                                 // the epilogue writes the last frame of its rows with plain 8-byte stores
     // stream-ahead conversion of the spectra by the two spare warps of every CTA (conv_D = 0: all done by the pre-pass)
     int conv_D;                  // task on bin f converts one slice of bin f + conv_D; bins < conv_D come from the pre-pass
     int nsl;                     // slices per bin = lt_groups * csize (one per CTA-task of a bin)
@@ -168,6 +186,10 @@ struct Params {
     int* done;                   // [F] CTA-tasks of the bin that have received all their planes
     int ring;                    // plane slots: bin f lives in slot f % ring (conv_D > 0); = F otherwise
     float* tail_part;            // [F][nsl][16] partial power sums of the tail rows
+    // Addition-theorem build (spherical-harmonic operators, see legendre block below): nullable
+    const unsigned* leg_devmag;  // [64] largest deviation of G_n from s_q (2n+1) P_n(x), [64] largest |G_n| (float bits)
+    const float2* leg_sq;        // [64] s_q = G_0[., q]
+    const float4* leg_xt;        // [ltiles][16][128] : x[l][4 j .. 4 j + 3] per lane l, x = cos of the angle (l, q)
     int debug;                   // timing attribution (SFA_DEBUG_HOOKS builds only): 1 no TMA stores, 2 no build FMAs,
                                  // 4 no staging writes, 8 no MMAs, 16 no operand loads, 32 converters read no X,
                                  // 64 converters write no planes
@@ -423,6 +445,16 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 #if SFA_FUSED_G2_HINT
         const uint64_t g2_pol = l2_policy_evict_last();
 #endif
+        // addition-theorem build: only if the preparation found every group product to follow the Legendre model
+        bool use_leg = false;
+        if (NG > 0 && NG <= kLegMaxGroups && prm.leg_xt != nullptr && prm.ngroups >= 2) {
+            use_leg = true;
+            for (int g = 0; g < prm.ngroups; ++g) {
+                const float dev = __uint_as_float(__ldg(prm.leg_devmag + g));
+                const float mag = __uint_as_float(__ldg(prm.leg_devmag + 64 + g));
+                if (!(dev <= kLegTol * mag)) use_leg = false;
+            }
+        }
         for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
             long long f;
             int lt;
@@ -455,7 +487,61 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     aim[2 * j + 1] = fmaf(dgv.y, v[j].z, aim[2 * j + 1]);
                 }
             };
-            if (NG > 0) {
+            if (NG > 0 && NG <= kLegMaxGroups && use_leg) {
+                // A[l, q] = s_q sum_n (2n + 1) d[n] P_n(x_lq): Legendre recurrence in registers, 16 entries at a time
+                constexpr int NGA = (NG > 0 && NG <= kLegMaxGroups) ? NG : 2;
+                float2 dg[NGA];
+#pragma unroll
+                for (int g = 0; g < NGA; ++g) {
+                    dg[g] = (g < prm.ngroups) ? ld_filter(prm.d + f * prm.ngroups + g) : make_float2(0.f, 0.f);
+                    dg[g].x *= (float)(2 * g + 1);
+                    dg[g].y *= (float)(2 * g + 1);
+                }
+                const float4* xr = prm.leg_xt + ((size_t)lt * 16 + (size_t)half * 8) * kTileL + row;
+                if (!(prm.debug & 2)) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float x[16], p0[16], p1[16];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 v = __ldg(xr + (size_t)(h * 4 + i) * kTileL);
+                            x[4 * i] = v.x;
+                            x[4 * i + 1] = v.y;
+                            x[4 * i + 2] = v.z;
+                            x[4 * i + 3] = v.w;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            p0[e] = 1.f;
+                            p1[e] = x[e];
+                            are[16 * h + e] = fmaf(dg[1].x, x[e], dg[0].x);
+                            aim[16 * h + e] = fmaf(dg[1].y, x[e], dg[0].y);
+                        }
+#pragma unroll
+                        for (int n = 1; n + 1 < NGA; ++n) {
+                            if (n + 1 < prm.ngroups) {
+                                const float ca = (float)(2 * n + 1) / (float)(n + 1), cb = (float)n / (float)(n + 1);
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) {
+                                    const float pn = fmaf(ca * x[e], p1[e], -cb * p0[e]);
+                                    p0[e] = p1[e];
+                                    p1[e] = pn;
+                                    are[16 * h + e] = fmaf(dg[n + 1].x, pn, are[16 * h + e]);
+                                    aim[16 * h + e] = fmaf(dg[n + 1].y, pn, aim[16 * h + e]);
+                                }
+                            }
+                        }
+                    }
+                    const float2* sq = prm.leg_sq + half * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float2 s = __ldg(sq + j);
+                        const float r = are[j], i = aim[j];
+                        are[j] = fmaf(r, s.x, -i * s.y);
+                        aim[j] = fmaf(r, s.y, i * s.x);
+                    }
+                }
+            } else if (NG > 0) {
                 // few groups (spherical arrays: one per order): the bin's filters sit in registers, loop unrolled
                 constexpr int NGA = NG > 0 ? NG : 1;
                 float2 dg[NGA];
@@ -550,6 +636,20 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         }
                     }
                     if (prm.no_store) continue;                                 // power map only (warp-uniform)
+                    if (prm.odd_last && prm.T - 1 >= t0 && prm.T - 1 < t0 + 32) {
+                        const int jj = (int)(prm.T - 1 - t0);
+                        uint32_t xr = 0u, xi = 0u;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j == jj) {
+                                xr = re[j];
+                                xi = im[j];
+                            }
+                        if (l0 + lane < prm.L)
+                            prm.out[(f * prm.Lrows + l0 + lane) * prm.ldo + prm.T - 1] =
+                                make_float2(__uint_as_float(xr), __uint_as_float(xi));
+                        if (t0 >= prm.Tst) continue;                            // the tile held that frame only
+                    }
                     unsigned char* const sbuf = my_store + (size_t)buf * 2 * kStoreBoxBytes;
                     // the stores issued from this slot kStoreRing passes ago must have finished reading it
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStoreRing - 1) : "memory");
@@ -571,11 +671,11 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     if (lane == 0 && !(prm.debug & 1)) {
                         if (st_hint) {
                             tma_store_3d_hint(&o_map, sbuf, (int)(2 * t0), l0, (int)f, st_pol);
-                            if (t0 + 16 < prm.T)
+                            if (t0 + 16 < prm.Tst)
                                 tma_store_3d_hint(&o_map, sbuf + kStoreBoxBytes, (int)(2 * (t0 + 16)), l0, (int)f, st_pol);
                         } else {
                             tma_store_3d(&o_map, sbuf, (int)(2 * t0), l0, (int)f, false);
-                            if (t0 + 16 < prm.T)
+                            if (t0 + 16 < prm.Tst)
                                 tma_store_3d(&o_map, sbuf + kStoreBoxBytes, (int)(2 * (t0 + 16)), l0, (int)f, false);
                         }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -897,7 +997,8 @@ __device__ __forceinline__ int order_of_col(int i) {     // radial.repeat_n_m: c
 // pairs so that the grid fills the machine.  Reads Y_Q as it is (no conjugate-transposed copy).
 __global__ void __launch_bounds__(kTileL)
 group_products_g2_kernel(const double2* __restrict__ YL, const double2* __restrict__ YQ, long long L, int Q, int M,
-                         int G, int per_order, int Kh, float4* __restrict__ out) {
+                         int G, int per_order, int Kh, float4* __restrict__ out, unsigned* __restrict__ devmag,
+                         float2* __restrict__ sq_out, float* __restrict__ xt) {
     extern __shared__ double2 sq[];                              // conj-free copy of Y_Q[q0 .. q1)[m0 .. m1): [q][nm]
     const int lane = threadIdx.x;
     const long long lt = blockIdx.x / G;
@@ -917,6 +1018,19 @@ group_products_g2_kernel(const double2* __restrict__ YL, const double2* __restri
         sq[i] = (q < Q) ? YQ[(long long)q * M + m0 + mm] : make_double2(0.0, 0.0);
     }
     __syncthreads();
+    // addition-theorem model (devmag != nullptr: per-order groups, M >= 4): s_q = Y_L[0, 0] conj(Y_Q[q, 0]),
+    // x_lq = Re(G_1[l, q] / (3 s_q)), model G_g[l, q] = s_q (2g + 1) P_g(x_lq); everything in FP64
+    const bool leg = devmag != nullptr;
+    double2 yl1 = make_double2(0.0, 0.0), yl2 = yl1, yl3 = yl1, y00 = yl1;
+    if (leg) {
+        y00 = YL[0];
+        if (l < L) {
+            yl1 = YL[l * M + 1];
+            yl2 = YL[l * M + 2];
+            yl3 = YL[l * M + 3];
+        }
+    }
+    double ldev = 0.0, lmag = 0.0;
     for (int j = j0; j < j1; ++j) {
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         if (l < L) {
@@ -933,6 +1047,49 @@ group_products_g2_kernel(const double2* __restrict__ YL, const double2* __restri
             }
         }
         o[(size_t)j * kTileL] = make_float4((float)s0, (float)s1, (float)s2, (float)s3);
+        if (leg && l < L) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int q = 2 * j + c;
+                if (q >= Q) continue;
+                const double gre = c ? s2 : s0, gim = c ? s3 : s1;
+                const double2* yq = YQ + (long long)q * M;
+                const double2 q0 = yq[0], q1 = yq[1], q2 = yq[2], q3 = yq[3];
+                const double sre = y00.x * q0.x + y00.y * q0.y, sim = y00.y * q0.x - y00.x * q0.y;       // y00 conj(q0)
+                const double g1re = yl1.x * q1.x + yl1.y * q1.y + yl2.x * q2.x + yl2.y * q2.y + yl3.x * q3.x + yl3.y * q3.y;
+                const double g1im = yl1.y * q1.x - yl1.x * q1.y + yl2.y * q2.x - yl2.x * q2.y + yl3.y * q3.x - yl3.x * q3.y;
+                const double den = 3.0 * (sre * sre + sim * sim);
+                double x = den > 0.0 ? (g1re * sre + g1im * sim) / den : 0.0;                            // Re(g1 / (3 s))
+                x = x > 1.0 ? 1.0 : (x < -1.0 ? -1.0 : x);
+                double p0 = 1.0, p1 = x;
+                for (int n = 1; n < g; ++n) {
+                    const double pn = ((2 * n + 1) * x * p1 - n * p0) / (n + 1);
+                    p0 = p1;
+                    p1 = pn;
+                }
+                const double pg = (g == 0 ? 1.0 : p1) * (2 * g + 1);
+                const double dre = fabs(gre - sre * pg), dim = fabs(gim - sim * pg);
+                // (a NaN compares false everywhere: fmax would drop it, so it is carried by hand)
+                if (!(dre <= ldev)) ldev = dre;
+                if (!(dim <= ldev)) ldev = dim;
+                lmag = fmax(lmag, fmax(fabs(gre), fabs(gim)));
+                if (g == 1) xt[(((size_t)lt * 16 + (q >> 2)) * kTileL + lane) * 4 + (q & 3)] = (float)x;
+                if (g == 0 && l == 0) sq_out[q] = make_float2((float)sre, (float)sim);
+            }
+        }
+    }
+    if (leg) {
+        // non-negative floats (and NaN, whose bits lie above +inf) order like their bit patterns
+        unsigned ud = __float_as_uint(fabsf((float)ldev)), um = __float_as_uint(fabsf((float)lmag));
+        if (ldev > 0.0 && ud == 0u) ud = 1u;                       // deviations below the float range still count
+        for (int off = 16; off; off >>= 1) {
+            ud = max(ud, __shfl_xor_sync(0xffffffffu, ud, off));
+            um = max(um, __shfl_xor_sync(0xffffffffu, um, off));
+        }
+        if ((lane & 31) == 0) {
+            atomicMax(devmag + g, ud);
+            atomicMax(devmag + 64 + g, um);
+        }
     }
 }
 
@@ -946,10 +1103,17 @@ bool pwd_fused_supported(long long L, long long Q, long long T, int Cd, long lon
 }
 
 // bytes of the builders' group-product table and of the pre-split spectra of `nf` bins
-size_t pwd_fused_g2_bytes(long long L, long long Q, int Cd) {
+static size_t fused_g2_table_bytes(long long L, long long Q, int Cd) {
     const long long ltiles = ceil_div(L, fused::kTileL);
     const long long Kh = ceil_div(Q, 8) * 4;
-    return (size_t)ltiles * Cd * Kh * fused::kTileL * sizeof(float4);
+    return ((size_t)ltiles * Cd * Kh * fused::kTileL * sizeof(float4) + 255) / 256 * 256;
+}
+static size_t fused_leg_bytes(long long L) {
+    return fused::kLegHdrBytes + (size_t)ceil_div(L, fused::kTileL) * 16 * fused::kTileL * sizeof(float4);
+}
+// group-product table + the addition-theorem block (deviation record, s_q, x table)
+size_t pwd_fused_g2_bytes(long long L, long long Q, int Cd) {
+    return fused_g2_table_bytes(L, Q, Cd) + fused_leg_bytes(L);
 }
 static size_t fused_planes_bytes(long long nf, long long Q, long long T) {
     const long long Kp = ceil_div(Q, 4) * 4;
@@ -975,8 +1139,16 @@ int launch_group_products_g2(const double2* YL, const double2* YQ, long long L, 
     const int nm_max = per_order ? 2 * Cd - 1 : 1;           // the largest group: order Cd - 1 has 2 Cd - 1 columns
     const size_t smem = (size_t)2 * jper * nm_max * sizeof(double2);
     if (smem > 48 * 1024) return SFA_ERR_UNSUPPORTED;
+    // addition-theorem block: zeroed (x = 0, s = 0 for padding rows / columns; deviations start at 0), or -- when the
+    // model does not apply -- a deviation record that can never pass (0x7f7f7f7f = 3.4e38 against 1e-8 * 3.4e38)
+    unsigned char* legb = reinterpret_cast<unsigned char*>(G2) + fused_g2_table_bytes(L, Q, Cd);
+    const bool leg = per_order && Cd >= 2 && Cd <= fused::kLegMaxGroups && M >= 4 && !options().no_legendre;
+    SFA_CUDA_CHECK(cudaMemsetAsync(legb, 0, fused_leg_bytes(L), st));
+    if (!leg) SFA_CUDA_CHECK(cudaMemsetAsync(legb, 0x7f, 128 * sizeof(unsigned), st));
     fused::group_products_g2_kernel<<<dim3((unsigned)(ltiles * Cd), (unsigned)ysplit), fused::kTileL, smem, st>>>(
-        YL, YQ, L, (int)Q, M, Cd, per_order, Kh, reinterpret_cast<float4*>(G2));
+        YL, YQ, L, (int)Q, M, Cd, per_order, Kh, reinterpret_cast<float4*>(G2),
+        leg ? reinterpret_cast<unsigned*>(legb) : nullptr, reinterpret_cast<float2*>(legb + 128 * sizeof(unsigned)),
+        reinterpret_cast<float*>(legb + fused::kLegHdrBytes));
     SFA_LAUNCH_CHECK();
     return SFA_OK;
 }
@@ -984,7 +1156,7 @@ int launch_group_products_g2(const double2* YL, const double2* YQ, long long L, 
 // q[f] = (sum_g d[f][g] G_g) X[f] for nf bins.  d: complex128 [nf][Cd]; X: [nf][Q][T]; out: [nf][L][ldo].
 int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd, const float* G2, const double2* d,
                      const float2* X, float* Xs, float2* out, long long ldo, float* power, int hybrid,
-                     cudaStream_t st) {
+                     cudaStream_t st, int pad_writable) {
     using namespace fused;
     if (nf <= 0) return SFA_OK;
     EncodeTiledFn encode = get_encode_fn();
@@ -1039,6 +1211,12 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     prm.X = X;
     prm.Xs = Xs;
     prm.G2_last = g2_last;
+    {
+        const unsigned char* legb = reinterpret_cast<const unsigned char*>(G2) + fused_g2_table_bytes(L, Q, Cd);
+        prm.leg_devmag = reinterpret_cast<const unsigned*>(legb);
+        prm.leg_sq = reinterpret_cast<const float2*>(legb + 128 * sizeof(unsigned));
+        prm.leg_xt = reinterpret_cast<const float4*>(legb + kLegHdrBytes);
+    }
     prm.out = out;
     prm.ldo = ldo;
     prm.Lm = Lmain;
@@ -1069,9 +1247,22 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
             return SFA_ERR_CUDA;
         }
         // beams as fp32 [nf][L][2*ldo]; store box = 32 rows x 32 fp32 (16 frames), SWIZZLE_128B staging
-        // (power map only: the map is encoded over the plane buffer and never used)
+        // (power map only: the map is encoded over the plane buffer and never used).
+        // Row ends: with T = 938 a row is 58.6 lines of 128 bytes, and a tensor map of extent T clips the last box
+        // of every row to a partial line -- which costs the WHOLE store stream 15-20 % of its bandwidth (pure-store
+        // probe, tools/store_probe5.cu: 4.76 TB/s with the clipped row ends, 5.74 TB/s with whole lines; the L2
+        // has to fetch the rest of a partially written line from DRAM before it can write it back).  When the
+        // caller owns the row padding (sfa_pwd_shape.out_pad_writable) the map extends to the next multiple of 16
+        // frames: the frames [T, T16) are written as zeros (the TMA load of the spectra zero-fills frames >= T).
+        const long long T16 = ceil_div(T, 16) * 16;
+        long long Tmap = (pad_writable && ldo >= T16) ? T16 : T;
+        // a TMA store clips in 16-byte units: an odd T (8 T bytes per row) would take frame T with it
+        prm.odd_last = (Tmap == T && (T & 1) && ldo > T) ? 1 : 0;
+        if (prm.odd_last) Tmap = T - 1;
+        prm.Tst = Tmap < T ? Tmap : T;
+        if (Tmap < 1) Tmap = 1;                                      // T = 1: every store is the epilogue's own
         void* const obase = out ? (void*)out : (void*)Xs;
-        cuuint64_t odim[3] = {(cuuint64_t)(2 * T), (cuuint64_t)Lmain, (cuuint64_t)nf};
+        cuuint64_t odim[3] = {(cuuint64_t)(2 * Tmap), (cuuint64_t)Lmain, (cuuint64_t)nf};
         cuuint64_t ostr[2] = {(cuuint64_t)ldo * 8, (cuuint64_t)L * ldo * 8};
         cuuint32_t obox[3] = {32, 32, 1};
         r = encode(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, obase, odim, ostr, obox, estr,

@@ -69,6 +69,8 @@ struct Options {
     int issuers;           // MMA issuer warps of the resident-K kernel (1 or 2)
     int old_build;         // steering build: generic kernel instead of the few-groups fast kernel
     int no_fused;          // steering form: slab build + GEMM launches instead of the fused persistent kernel
+    int no_legendre;       // fused kernel: always build the steering tile from the group-product table, even when the
+                           // operators are spherical-harmonic matrices (addition theorem, see pwd_fused_sm100.cu)
     int fused_prepass;     // fused kernel: split ALL spectra in the pre-pass kernel (no in-kernel stream-ahead conversion)
     int no_dmma;           // complex128 path: CUDA-core FMA tile kernel instead of the FP64 tensor-core (DMMA) kernel
     int fft_generic;       // irfft / stft: the generic radix-4 ping-pong kernel instead of the radix-16 fast path

@@ -43,6 +43,7 @@ static Options make_options() {
     o.old_build = env_flag("SFA_OLD_BUILD");
     o.no_fused = env_flag("SFA_NO_FUSED");
     o.fused_prepass = env_flag("SFA_FUSED_PREPASS");
+    o.no_legendre = env_flag("SFA_NO_LEGENDRE");
     o.no_dmma = env_flag("SFA_NO_DMMA");
     o.fft_generic = env_flag("SFA_FFT_GENERIC");
     o.reserve_sms = (int)env_num("SFA_RESERVE_SMS", 0.0);
@@ -194,6 +195,7 @@ static double* option_slot(const char* key, int** islot) {
     else if (!strcmp(key, "old_build")) *islot = &o.old_build;
     else if (!strcmp(key, "no_fused")) *islot = &o.no_fused;
     else if (!strcmp(key, "fused_prepass")) *islot = &o.fused_prepass;
+    else if (!strcmp(key, "no_legendre")) *islot = &o.no_legendre;
     else if (!strcmp(key, "no_dmma")) *islot = &o.no_dmma;
     else if (!strcmp(key, "fft_generic")) *islot = &o.fft_generic;
     else if (!strcmp(key, "reserve_sms")) *islot = &o.reserve_sms;

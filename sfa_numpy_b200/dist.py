@@ -124,6 +124,8 @@ class OverlappedPwd:
             dev, cdtype, ld = self.plan.dev, self.plan.cdtype, steering._padded_pitch(int(T))
         else:
             self.plan, dev, cdtype, ld = make_plan(Y_look, dn[: self.cb], Y_mic, T)
+        # `buf` is this object's own row-padded allocation: the kernels may complete the last line of every row
+        self._plan_kw = {"pad_writable": True} if make_plan is None else {}
         self.buf = torch.empty((F, L, ld), dtype=cdtype, device=dev)          # row-padded; gathered with its padding
         self.full = self.buf[:, :, : self.T]
         self.comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
@@ -155,7 +157,7 @@ class OverlappedPwd:
         for c in range(self.pieces):
             f0 = self.block_start(c)
             self.plan.dn = self.dn[f0:f0 + cb]
-            self.plan(X_loc[c * cb:(c + 1) * cb], out=self.full[f0:f0 + cb])
+            self.plan(X_loc[c * cb:(c + 1) * cb], out=self.full[f0:f0 + cb], **self._plan_kw)
             ev = torch.cuda.Event()
             ev.record()
             mine = self.buf[f0:f0 + cb]
@@ -182,7 +184,7 @@ class OverlappedPwd:
         for c in range(self.pieces):
             f0 = self.block_start(c)
             self.plan.dn = self.dn[f0:f0 + cb]
-            self.plan(X_loc[c * cb:(c + 1) * cb], out=self.full[f0:f0 + cb])
+            self.plan(X_loc[c * cb:(c + 1) * cb], out=self.full[f0:f0 + cb], **self._plan_kw)
             if W == 1:
                 continue
             slab = self.buf[c * W * cb:(c + 1) * W * cb]

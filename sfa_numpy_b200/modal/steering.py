@@ -61,10 +61,25 @@ def _padded_pitch(T):
     return T if T <= 128 or T % 32 == 0 else (T + 31) // 32 * 32
 
 
+_PAD_ATTR = "_sfa_row_pad_owned"
+
+
 def _alloc_out(F, L, T, cdtype, dev):
     ld = _padded_pitch(T)
     buf = torch.empty((F, L, ld), dtype=cdtype, device=dev)
-    return buf[:, :, :T] if ld != T else buf
+    if ld == T:
+        return buf
+    # the padding frames [T, ld) of every row belong to this library: the kernels may complete the last 128-byte
+    # line of a row with zeros (sfa_pwd_shape.out_pad_writable), which HBM absorbs 15-20 % faster than a partial line
+    view = buf[:, :, :T]
+    setattr(view, _PAD_ATTR, True)
+    return view
+
+
+def _pad_owned(out):
+    """True for the row-padded views made by `empty_beams` / `pwd` themselves (a slice of one is a new tensor
+    object and does not carry the mark: the kernels then leave everything beyond frame T alone)."""
+    return bool(getattr(out, _PAD_ATTR, False))
 
 
 def empty_beams(F, L, T, dtype=torch.complex64, device=None):
@@ -148,6 +163,7 @@ def pwd(Y_look, dn, Y_mic, p, precision=None, form="auto", out=None):
         out = _alloc_out(F, L, T, cdtype, dev)
     if F > 0 and L > 0:
         shape.out_ld = _check_out(out, F, L, T, cdtype, dev)
+        shape.out_pad_writable = 1 if _pad_owned(out) else 0
     nbytes = lib.sfa_pwd_work_bytes(ctypes.byref(shape))
     if nbytes == 0:
         raise ValueError("unsupported plane-wave-decomposition shape")
@@ -230,8 +246,10 @@ class PwdPlan:
                                                 _lib.ptr(self.work), self.nbytes, _lib.stream_ptr(self.dev)))
         self._prepared_ld = self.shape.out_ld
 
-    def __call__(self, X, out=None, power=None, beams=True):
-        """``beams=False`` (with `power`): only the beam power map is produced -- the fused steering kernel skips its
+    def __call__(self, X, out=None, power=None, beams=True, pad_writable=None):
+        """``pad_writable``: whether the kernels may overwrite the row padding of `out` (frames [T, stride(1)) of
+        every row) -- default: only for the row-padded tensors of `empty_beams`; pass True for a slice of one.
+        ``beams=False`` (with `power`): only the beam power map is produced -- the fused steering kernel skips its
         stores, the 8 F L T bytes of beams never reach memory; returns the map.  Needs a plan that runs the fused
         kernel (complex64 precisions, steering form, at most 64 microphones), otherwise ValueError."""
         if X.dtype != self.cdtype or not X.is_contiguous() or X.device != self.dev:
@@ -254,6 +272,7 @@ class PwdPlan:
             if out is None:
                 out = _alloc_out(*self.out_shape, self.cdtype, self.dev)
             ld = _check_out(out, *self.out_shape, self.cdtype, self.dev)
+            self.shape.out_pad_writable = 1 if (_pad_owned(out) if pad_writable is None else pad_writable) else 0
         # the plan (kernel choice, workspace layout) depends on the row pitch of `out`: prepare again if it changed
         if self._prepared_ld is None or ld != self.shape.out_ld:
             self.shape.out_ld = ld

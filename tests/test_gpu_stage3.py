@@ -347,6 +347,16 @@ def test_pwd_fused_kernel_shapes(mic, precision):
         Xd = torch.from_numpy(X).cuda()
         q_f = S.pwd(Yq_ref, dn_ref, Yp_ref, Xd, precision=precision, form="steering")
         assert bin_err(cpu(q_f), ref) < TOL64, ("fused", N, Q, L, F, T, bin_err(cpu(q_f), ref))
+        # spherical-harmonic operators: the builders take the addition-theorem (Legendre) path; the same call with
+        # the group-product table forced must agree with the oracle too -- and differ in the last bits, which
+        # shows that the two calls did take different paths
+        try:
+            _lib.check(lib.sfa_set_option(b"no_legendre", 1.0))
+            q_g = S.pwd(Yq_ref, dn_ref, Yp_ref, Xd, precision=precision, form="steering")
+        finally:
+            lib.sfa_set_option(b"no_legendre", 0.0)
+        assert bin_err(cpu(q_g), ref) < TOL64, ("fused, table", N, Q, L, F, T, bin_err(cpu(q_g), ref))
+        assert not torch.equal(q_f, q_g), ("Legendre path not taken", N, Q, L, F, T)
         try:
             _lib.check(lib.sfa_set_option(b"no_fused", 1.0))
             q_s = S.pwd(Yq_ref, dn_ref, Yp_ref, Xd, precision=precision, form="steering")
@@ -464,3 +474,103 @@ def test_pwd_power_map_only(mic):
     plan = S.PwdPlan(Yq, dn, Yp, T, precision="c64_fast", form="factored")
     with pytest.raises(ValueError):
         plan(X, power=True, beams=False)
+
+
+@pytest.mark.parametrize("precision", ["c64_fast", "c64"])
+def test_pwd_row_padding_contract(mic, precision):
+    """sfa_pwd_shape.out_pad_writable: with the flag (the library's own row-padded tensors, `empty_beams`) the fused
+    kernel completes the last 128-byte line of every row -- frames [T, roundup(T, 16)) become zeros, nothing
+    beyond is touched; without it (a caller's view of a wider tensor) nothing beyond frame T changes.  The beams
+    themselves are bit-equal either way."""
+    import torch
+    from sfa_numpy_b200 import _lib
+    lib = _lib.load()
+    A, R, S = mic.modal.angular, mic.modal.radial, mic.modal.steering
+    rng = np.random.default_rng(5)
+    for (N, Q, L, F, T) in ((3, 16, 300, 3, 138), (4, 25, 130, 40, 200), (8, 64, 2562, 2, 938), (2, 9, 200, 2, 131),
+                            (2, 9, 130, 3, 193), (3, 16, 128, 2, 257)):
+        az, co, w = O.fibonacci_grid(Q)
+        azl, col, _ = O.fibonacci_grid(L)
+        Yp, Yq = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
+        k = O.wavenumbers(128)[:F] + 0.5
+        dn, _ = O.regularize(1 / O.spherical_pw(N, k, 0.042, "rigid"), 100, "Tikh")
+        X = (rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(np.complex64)
+        Xd = torch.from_numpy(X).cuda()
+        ld, T16 = S._padded_pitch(T), (T + 15) // 16 * 16
+        assert ld >= T16 > T
+        plan = S.PwdPlan(Yq, dn, Yp, T, precision=precision, form="steering")
+        # (1) a caller's view: the sentinel beyond frame T survives (also through the slab build + GEMM pipeline)
+        big = torch.full((F, L, ld), 7.0 + 3.0j, dtype=torch.complex64, device="cuda")
+        q_view = plan(Xd, out=big[:, :, :T])
+        assert bool((big[:, :, T:] == 7.0 + 3.0j).all()), (N, Q, L, F, T)
+        for form in ("steering", "factored"):
+            try:
+                _lib.check(lib.sfa_set_option(b"no_fused", 1.0))
+                big2 = torch.full((F, L, ld), 7.0 + 3.0j, dtype=torch.complex64, device="cuda")
+                q2 = S.pwd(Yq, dn, Yp, Xd, precision=precision, form=form, out=big2[:, :, :T])
+            finally:
+                lib.sfa_set_option(b"no_fused", 0.0)
+            assert bool((big2[:, :, T:] == 7.0 + 3.0j).all()), ("no_fused", form, N, Q, L, F, T)
+            assert bin_err(cpu(q2), cpu(q_view).astype(np.complex128)) < TOL64
+        # (2) the library's own padded tensor: zeros up to the next multiple of 16 frames, the rest untouched
+        own = S.empty_beams(F, L, T, torch.complex64, torch.device("cuda"))
+        base = own._base if own._base is not None else own
+        base.fill_(7.0 + 3.0j)
+        q_own = plan(Xd, out=own)
+        main = (L // 128) * 128 if (L % 128 and L % 128 <= 16 and L > 128) else L        # tail rows: plain stores
+        assert bool((base[:, :main, T:T16] == 0).all()), (N, Q, L, F, T)
+        assert bool((base[:, :, T16:] == 7.0 + 3.0j).all()) and bool((base[:, main:, T:] == 7.0 + 3.0j).all())
+        assert torch.equal(q_own, q_view)
+        ref = O.pwd_factored(Yq, O.repeat_n_m(dn), Yp, X.astype(np.complex128))
+        assert bin_err(cpu(q_own), ref) < TOL64
+        # (3) a slice of an owned tensor does not carry the mark unless the caller says so
+        sl = own[:, :, :]
+        assert not S._pad_owned(sl) and S._pad_owned(own)
+
+
+@pytest.mark.parametrize("precision", ["c64_fast", "c64"])
+def test_pwd_fused_operator_structure_detection(mic, precision):
+    """The addition-theorem build of the fused kernel is taken only when the preparation has verified, in FP64, that
+    every group product follows s_q (2n+1) P_n(x_lq).  Operators that are not spherical-harmonic matrices --
+    random complex matrices with per-order filters, SH matrices with one perturbed entry, SH matrices with rows of
+    Y_look rescaled -- must run through the group-product table: correct against the oracle and BIT-equal to a run
+    with the Legendre path switched off.  SH matrices with complex weights folded into Y_mic still qualify."""
+    import torch
+    from sfa_numpy_b200 import _lib
+    S = mic.modal.steering
+    lib = _lib.load()
+    rng = np.random.default_rng(23)
+
+    def both(Yq, dn, Yp, Xd):
+        q1 = S.pwd(Yq, dn, Yp, Xd, precision=precision, form="steering")
+        try:
+            _lib.check(lib.sfa_set_option(b"no_legendre", 1.0))
+            q2 = S.pwd(Yq, dn, Yp, Xd, precision=precision, form="steering")
+        finally:
+            lib.sfa_set_option(b"no_legendre", 0.0)
+        return q1, q2
+
+    for (N, Q, L, F, T) in ((3, 16, 300, 4, 96), (8, 64, 515, 3, 130), (1, 4, 140, 2, 70)):
+        M = (N + 1) ** 2
+        az, co, w = O.fibonacci_grid(Q)
+        azl, col, _ = O.fibonacci_grid(L)
+        Yp_sh, Yq_sh = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
+        dn = rng.standard_normal((F, N + 1)) + 1j * rng.standard_normal((F, N + 1))
+        X = (rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(np.complex64)
+        Xd = torch.from_numpy(X).cuda()
+        Yq_rand = rng.standard_normal((L, M)) + 1j * rng.standard_normal((L, M))
+        Yp_rand = rng.standard_normal((Q, M)) + 1j * rng.standard_normal((Q, M))
+        Yq_pert = Yq_sh.copy()
+        Yq_pert[L // 2, M - 1] *= 1.0 + 1e-6
+        Yq_rows = Yq_sh * (1.0 + 0.5 * rng.random((L, 1)))
+        for name, Yq, Yp in (("random", Yq_rand, Yp_rand), ("perturbed", Yq_pert, Yp_sh), ("row-scaled", Yq_rows, Yp_sh)):
+            ref = O.pwd_factored(Yq, O.repeat_n_m(dn), Yp, X.astype(np.complex128))
+            q1, q2 = both(Yq, dn, Yp, Xd)
+            assert bin_err(cpu(q1), ref) < TOL64, (name, N, Q, L, F, T, bin_err(cpu(q1), ref))
+            assert torch.equal(q1, q2), (name, "took the Legendre path", N, Q, L, F, T)
+        # complex column weights on the microphone side keep the structure (s_q becomes complex)
+        Yp_cw = Yp_sh * np.exp(1j * rng.random((Q, 1)))
+        ref = O.pwd_factored(Yq_sh, O.repeat_n_m(dn), Yp_cw, X.astype(np.complex128))
+        q1, q2 = both(Yq_sh, dn, Yp_cw, Xd)
+        assert bin_err(cpu(q1), ref) < TOL64 and bin_err(cpu(q2), ref) < TOL64
+        assert not torch.equal(q1, q2), ("complex weights: Legendre path not taken", N, Q, L, F, T)
