@@ -63,6 +63,10 @@ constexpr int kEpiWarp0 = 4, kEpiWarps = 4;
 constexpr int kBuildWarp0 = 8, kBuildWarps = 8;
 constexpr int kThreads = 512;
 constexpr int kRegsCtl = 56, kRegsEpi = 104, kRegsBuild = 176;   // 128 * (56 + 104) + 256 * 176 = 65536
+constexpr int kG2Batch = 16;                                     // group-product loads in flight per builder thread
+// (Tried: the epilogue warps pulling the WHOLE accumulator tile into registers -- 152 registers each, 152 for the
+// builders -- so that the accumulator goes back to the MMA warp before any staging: no gain, 5.37 against 5.21 ms.
+// Clusters of four CTAs sharing one bin's plane stream -- half the L2 reads of the planes -- : 6.2 against 5.6 ms.)
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 2 * kTileT;                // Re + Im per accumulator stage
 constexpr int kOperandCol0 = 2 * kAccCols;          // 256
@@ -294,7 +298,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                             unsigned char* dbox = dst + (pl * 2 + kb) * kBoxBytes;
                             if (csize == 1) {
                                 tma_load_3d(&x_map, &bars->b_full[stage], dbox, kb * kBoxK, tt * kTileT, fslot * 4 + pl);
-                            } else if (((prm.kboxes > 1 ? pl * 2 + kb : pl) & 1) == (int)crank) {
+                            } else if (((prm.kboxes > 1 ? pl * 2 + kb : pl) % csize) == (int)crank) {
                                 tma_load_3d_mc(&x_map, &bars->b_full[stage], dbox, kb * kBoxK, tt * kTileT, fslot * 4 + pl, cmask);
                             }
                         }
@@ -319,7 +323,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 #pragma unroll
                                 for (int kb = 0; kb < 2; ++kb) {
                                     if (kb >= prm.kboxes) continue;
-                                    if (csize == 1 || ((prm.kboxes > 1 ? pl * 2 + kb : pl) & 1) == (int)crank)
+                                    if (csize == 1 || ((prm.kboxes > 1 ? pl * 2 + kb : pl) % csize) == (int)crank)
                                         tma_prefetch_3d(&x_map, kb * kBoxK, ptt * kTileT, (pf % prm.ring) * 4 + pl);
                                 }
                             }
@@ -466,25 +470,31 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             const float4* gp = prm.G2 + ((size_t)lt * prm.ngroups * prm.Kh + (size_t)half * 16) * kTileL + row;
             // one group: are/aim += d_f[g] * G_g[row, this warp's 32 mic columns]
             auto add_group = [&](const float2 dgv, const float4* gg) {
-                // all 16 loads of the group are issued before the first FMA (memory-level parallelism)
-                float4 v[16];
+                // all loads of a batch are issued before its first FMA (memory-level parallelism)
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
+                for (int j0 = 0; j0 < 16; j0 += kG2Batch) {
+                    float4 v[kG2Batch];
+#pragma unroll
+                    for (int jj = 0; jj < kG2Batch; ++jj) {
+                        const int j = j0 + jj;
 #if SFA_FUSED_G2_HINT
-                    v[j] = (j < npairs) ? ldg_hint(gg + (size_t)j * kTileL, g2_pol) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[jj] = (j < npairs) ? ldg_hint(gg + (size_t)j * kTileL, g2_pol) : make_float4(0.f, 0.f, 0.f, 0.f);
 #else
-                    v[j] = (j < npairs) ? __ldg(gg + (size_t)j * kTileL) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[jj] = (j < npairs) ? __ldg(gg + (size_t)j * kTileL) : make_float4(0.f, 0.f, 0.f, 0.f);
 #endif
+                    }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    are[2 * j] = fmaf(dgv.x, v[j].x, are[2 * j]);
-                    are[2 * j] = fmaf(-dgv.y, v[j].y, are[2 * j]);
-                    aim[2 * j] = fmaf(dgv.x, v[j].y, aim[2 * j]);
-                    aim[2 * j] = fmaf(dgv.y, v[j].x, aim[2 * j]);
-                    are[2 * j + 1] = fmaf(dgv.x, v[j].z, are[2 * j + 1]);
-                    are[2 * j + 1] = fmaf(-dgv.y, v[j].w, are[2 * j + 1]);
-                    aim[2 * j + 1] = fmaf(dgv.x, v[j].w, aim[2 * j + 1]);
-                    aim[2 * j + 1] = fmaf(dgv.y, v[j].z, aim[2 * j + 1]);
+                    for (int jj = 0; jj < kG2Batch; ++jj) {
+                        const int j = j0 + jj;
+                        are[2 * j] = fmaf(dgv.x, v[jj].x, are[2 * j]);
+                        are[2 * j] = fmaf(-dgv.y, v[jj].y, are[2 * j]);
+                        aim[2 * j] = fmaf(dgv.x, v[jj].y, aim[2 * j]);
+                        aim[2 * j] = fmaf(dgv.y, v[jj].x, aim[2 * j]);
+                        are[2 * j + 1] = fmaf(dgv.x, v[jj].z, are[2 * j + 1]);
+                        are[2 * j + 1] = fmaf(-dgv.y, v[jj].w, are[2 * j + 1]);
+                        aim[2 * j + 1] = fmaf(dgv.x, v[jj].w, aim[2 * j + 1]);
+                        aim[2 * j + 1] = fmaf(dgv.y, v[jj].z, aim[2 * j + 1]);
+                    }
                 }
             };
             if (NG > 0 && NG <= kLegMaxGroups && use_leg) {
@@ -797,6 +807,15 @@ __device__ __forceinline__ void convert_slice(const Params& prm, unsigned char* 
                             xi = __uint_as_float(pack_bf16(xi, hi));
                         }
                         float* o = base + t * Kp + q;
+#ifdef SFA_DEBUG_HOOKS
+                        if (prm.debug & 1024) {                 // plane stores without the evict_last policy
+                            o[0] = hr;
+                            o[plane] = hi;
+                            o[2 * plane] = xr;
+                            o[3 * plane] = xi;
+                            continue;
+                        }
+#endif
                         st_f32_hint(o, hr, keep);
                         st_f32_hint(o + plane, hi, keep);
                         st_f32_hint(o + 2 * plane, xr, keep);
@@ -1122,7 +1141,7 @@ static size_t fused_planes_bytes(long long nf, long long Q, long long T) {
 static size_t fused_ready_bytes(long long nf) { return ((size_t)2 * nf * sizeof(int) + 255) / 256 * 256; }   // ready + done
 // split planes + hand-over counters + partial power sums of the tail rows (stream-ahead conversion)
 size_t pwd_fused_xs_bytes(long long nf, long long L, long long Q, long long T) {
-    const long long max_slices = ceil_div(L, fused::kTileL) + 2;
+    const long long max_slices = ceil_div(L, fused::kTileL) + 4;     // slices per bin <= l-tiles rounded up to the cluster size
     return fused_planes_bytes(nf, Q, T) + fused_ready_bytes(nf) +
            (size_t)nf * max_slices * fused::kTailMaxRows * sizeof(float);
 }
@@ -1187,6 +1206,9 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     prm.groups = nf * prm.lt_groups;
     prm.power = power;
     prm.store_evict_first = ((double)nf * (double)L * (double)ldo * 8.0 > 256e6) ? 1 : 0;     // >> L2 (126 MB)
+#ifdef SFA_DEBUG_HOOKS
+    if (options().fused_debug & 512) prm.store_evict_first = 0;
+#endif
     prm.no_store = out ? 0 : 1;
     if (!out && !power) return SFA_ERR_INVALID;
     const long long max_clusters = persistent_sms() / prm.csize;
@@ -1195,12 +1217,15 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     // the grid works on at once, plus two of slack; the first D bins come from the pre-pass.  Only worth it when
     // the launch covers several rounds of bins.
     const long long in_flight = ceil_div(n_clusters, prm.lt_groups);
-    long long D = options().fused_D > 0 ? options().fused_D : 2 * in_flight;
+    // (look-ahead of ONE round of bins and a ring of three rounds measured best on the headline shape: 5.0 ms per step
+    // against 5.6 ms with two rounds ahead and five rounds of planes -- the smaller ring leaves more of the L2 to the
+    // store stream; tools/fused_knobs.py)
+    long long D = options().fused_D > 0 ? options().fused_D : in_flight;
     if (options().fused_prepass || nf < 2 * D) D = 0;
     prm.conv_D = (int)D;
     // plane slots: the bins reuse a ring of D + 2 rounds of bins, so the planes are overwritten while still dirty in
     // L2 and never written back: DRAM sees X once and the beams once
-    long long ring = D + 3 * in_flight;
+    long long ring = D + 2 * in_flight;
     if (options().fused_ring > 0) ring = options().fused_ring > D ? options().fused_ring : D + 1;
     if (D <= 0 || ring >= nf) ring = nf;
     prm.ring = (int)ring;
