@@ -67,6 +67,25 @@ constexpr int kG2Batch = 16;                                     // group-produc
 // (Tried: the epilogue warps pulling the WHOLE accumulator tile into registers -- 152 registers each, 152 for the
 // builders -- so that the accumulator goes back to the MMA warp before any staging: no gain, 5.37 against 5.21 ms.
 // Clusters of four CTAs sharing one bin's plane stream -- half the L2 reads of the planes -- : 6.2 against 5.6 ms.)
+// CTA-pair mode (k2: tcgen05.mma.cta_group::2, M = 256 = the two l-tiles of a pair): every CTA holds HALF of the
+// frame tile (32 frames) of every plane, so an operand stage is 32 KB instead of 64 KB, the TMA writes and the
+// tensor core's B reads of a CTA's shared memory halve, and the freed 64 KB go into a third operand stage and a
+// third store slot per epilogue warp.  Bit-equal to the default mode on every shape tested (same MMA sequence per
+// output element) -- and SLOWER: 6.2-6.4 ms per step on the headline shape against 4.7-4.8 ms on the same box, whatever
+// the split of the freed shared memory (3 stages + 3 slots, 4 + 2, 2 + 4).  One MMA stream for two CTAs locks the
+// pair together: the leader cannot start a tile before BOTH epilogues have handed the accumulator back and both
+// builders have written their operand, so every hiccup of either store stream stalls both SMs, where the default
+// mode couples the two CTAs only through the release of an operand stage.  Kept behind the "fused_pair" option.
+#ifndef SFA_FUSED_STAGES2
+#define SFA_FUSED_STAGES2 3
+#endif
+#ifndef SFA_FUSED_RING2
+#define SFA_FUSED_RING2 3
+#endif
+constexpr int kStages2 = SFA_FUSED_STAGES2;
+constexpr int kStoreRing2 = SFA_FUSED_RING2;
+constexpr int kMaxStages = 4;
+static_assert(kStages <= kMaxStages && kStages2 <= kMaxStages, "barrier block");
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 2 * kTileT;                // Re + Im per accumulator stage
 constexpr int kOperandCol0 = 2 * kAccCols;          // 256
@@ -200,8 +219,8 @@ struct Params {
 };
 
 struct __align__(8) Barriers {
-    uint64_t b_full[kStages];
-    uint64_t b_empty[kStages];
+    uint64_t b_full[kMaxStages];
+    uint64_t b_empty[kMaxStages];
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
     uint64_t a_full;
@@ -210,15 +229,20 @@ struct __align__(8) Barriers {
     uint32_t pad;
 };
 
-template <bool kHybrid, int NG>
+template <bool kHybrid, int NG, bool k2>
 __global__ void __launch_bounds__(kThreads, 1)
 pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap o_map,
                  const Params prm) {
+    constexpr int kSt = k2 ? kStages2 : kStages;                         // operand stages
+    constexpr int kBoxB = k2 ? kBoxBytes / 2 : kBoxBytes;                // one (plane, k-box) of a stage: 32 / 64 frames
+    constexpr int kStageB = 8 * kBoxB;
+    constexpr int kRing = k2 ? kStoreRing2 : kStoreRing;                 // store slots per epilogue warp
+    constexpr int kStoreWarpB = kRing * 2 * kStoreBoxBytes;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    unsigned char* stage_base = smem;                                   // kStages x 64 KB
-    unsigned char* store_base = smem + (size_t)kStages * kStageBytes;   // 4 x 16 KB
-    Barriers* bars = reinterpret_cast<Barriers*>(store_base + kEpiWarps * kStoreWarpBytes);
+    unsigned char* stage_base = smem;                                   // kSt x 64 KB (32 KB in pair mode)
+    unsigned char* store_base = smem + (size_t)kSt * kStageB;           // 4 x 16 KB (24 KB)
+    Barriers* bars = reinterpret_cast<Barriers*>(store_base + kEpiWarps * kStoreWarpB);
     unsigned char* conv_base = reinterpret_cast<unsigned char*>(bars) + 256;      // converter warps' tile (conv_D > 0 only)
 
     const int warp = threadIdx.x >> 5;
@@ -229,23 +253,33 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     const long long cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        // pair mode: ONE MMA issuer (the leader, rank 0) for both CTAs.  Its barriers collect the arrivals of both
+        // CTAs (builders: a_full, epilogue warps: acc_empty, TMA bytes of both halves: b_full); its commits are
+        // multicast to the barriers of both (b_empty, acc_full, a_empty)
+        for (int s = 0; s < kSt; ++s) {
             mbar_init(&bars->b_full[s], 1);
-            mbar_init(&bars->b_empty[s], csize);        // the MMA issuer of every CTA in the cluster
+            mbar_init(&bars->b_empty[s], k2 ? 1 : csize);    // the MMA issuer of every CTA in the cluster
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->acc_full[a], 1);
-            mbar_init(&bars->acc_empty[a], kEpiWarps);
+            mbar_init(&bars->acc_empty[a], k2 ? 2 * kEpiWarps : kEpiWarps);
         }
-        mbar_init(&bars->a_full, kBuildWarps);
+        mbar_init(&bars->a_full, k2 ? 2 * kBuildWarps : kBuildWarps);
         mbar_init(&bars->a_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(&bars->tmem_base)),
-                     "r"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (k2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(&bars->tmem_base)),
+                         "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(&bars->tmem_base)),
+                         "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -280,30 +314,36 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 }
                 for (int tt = 0; tt < prm.t_tiles; ++tt) {
                     mbar_wait(&bars->b_empty[stage], phase ^ 1);
-                    unsigned char* dst = stage_base + (size_t)stage * kStageBytes;
+                    unsigned char* dst = stage_base + (size_t)stage * kStageB;
                     if (prm.debug & 16) {
-                        mbar_arrive(&bars->b_full[stage]);
-                        if (++stage == kStages) {
+                        if (!k2 || crank == 0) mbar_arrive(&bars->b_full[stage]);
+                        if (++stage == kSt) {
                             stage = 0;
                             phase ^= 1;
                         }
                         continue;
                     }
-                    mbar_arrive_expect_tx(&bars->b_full[stage], (uint32_t)(4 * prm.kboxes * kBoxBytes));
+                    // pair mode: the leader's barrier expects the bytes of BOTH halves (the peer's loads complete
+                    // on it; they may land before this arrive -- the phase cannot end without it)
+                    if (!k2) mbar_arrive_expect_tx(&bars->b_full[stage], (uint32_t)(4 * prm.kboxes * kBoxB));
+                    else if (crank == 0) mbar_arrive_expect_tx(&bars->b_full[stage], (uint32_t)(2 * 4 * prm.kboxes * kBoxB));
 #pragma unroll
                     for (int pl = 0; pl < 4; ++pl) {
 #pragma unroll
                         for (int kb = 0; kb < 2; ++kb) {
                             if (kb >= prm.kboxes) continue;
-                            unsigned char* dbox = dst + (pl * 2 + kb) * kBoxBytes;
-                            if (csize == 1) {
+                            unsigned char* dbox = dst + (pl * 2 + kb) * kBoxB;
+                            if (k2) {
+                                tma_load_3d_2sm(&x_map, &bars->b_full[stage], dbox, kb * kBoxK,
+                                                tt * kTileT + (int)crank * (kTileT / 2), fslot * 4 + pl);
+                            } else if (csize == 1) {
                                 tma_load_3d(&x_map, &bars->b_full[stage], dbox, kb * kBoxK, tt * kTileT, fslot * 4 + pl);
                             } else if (((prm.kboxes > 1 ? pl * 2 + kb : pl) % csize) == (int)crank) {
                                 tma_load_3d_mc(&x_map, &bars->b_full[stage], dbox, kb * kBoxK, tt * kTileT, fslot * 4 + pl, cmask);
                             }
                         }
                     }
-                    if (++stage == kStages) {
+                    if (++stage == kSt) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -338,17 +378,19 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         const int t_tail16 = ((t_tail + 15) >> 4) << 4;
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0, a_phase = 0;
-        for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
+        // pair mode: the leader issues for both CTAs (M = 256: its own l-tile and the peer's, each in its own tensor
+        // memory; N = 64 frames, 32 from each CTA's shared memory); the peer's warp 1 has nothing to do
+        for (long long grp = cluster_id; grp < prm.groups && !(k2 && crank != 0); grp += n_clusters) {
             long long f;
             int lt;
             decode(grp, f, lt);
-            if (lt >= prm.ltiles) {
+            if (!k2 && lt >= prm.ltiles) {
                 // ghost tile: consume the multicast stream, compute nothing
                 for (int tt = 0; tt < prm.t_tiles; ++tt) {
                     mbar_wait(&bars->b_full[stage], phase);
                     if (elect_one_sync()) tcgen05_commit_mc(&bars->b_empty[stage], cmask);
                     __syncwarp();
-                    if (++stage == kStages) {
+                    if (++stage == kSt) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -361,13 +403,16 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                 mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
                 mbar_wait(&bars->b_full[stage], phase);
                 tcgen05_fence_after();
-                const int n_mma = (tt == prm.t_tiles - 1) ? t_tail16 : kTileT;
-                const uint32_t idesc = make_idesc(kTileL, n_mma, false);
-                const uint32_t idesc_neg = make_idesc(kTileL, n_mma, true);
-                const uint32_t idesc_bf = make_idesc(kTileL, n_mma, false, true);
-                const uint32_t idesc_bf_neg = make_idesc(kTileL, n_mma, true, true);
+                // (pair mode: always all 64 frames -- the halves of the two CTAs are fixed at 32 frames each; the
+                // frames beyond T are zeros)
+                const int n_mma = (tt == prm.t_tiles - 1 && !k2) ? t_tail16 : kTileT;
+                constexpr int kM = k2 ? 2 * kTileL : kTileL;
+                const uint32_t idesc = make_idesc(kM, n_mma, false);
+                const uint32_t idesc_neg = make_idesc(kM, n_mma, true);
+                const uint32_t idesc_bf = make_idesc(kM, n_mma, false, true);
+                const uint32_t idesc_bf_neg = make_idesc(kM, n_mma, true, true);
                 if (elect_one_sync()) {
-                    const uint32_t sbase = smem_u32(stage_base + (size_t)stage * kStageBytes);
+                    const uint32_t sbase = smem_u32(stage_base + (size_t)stage * kStageB);
                     const uint64_t bdesc = make_b_desc(sbase);
                     const uint32_t d_re = tmem + acc * kAccCols;
                     const uint32_t d_im = d_re + kTileT;
@@ -389,12 +434,24 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                                 if ((prm.debug & 256) && pass == 0 && (ks & 1)) continue;
 #endif
                                 const int kb = ks >> 2, kk = ks & 3;
-                                const uint64_t b_re = bdesc + (uint64_t)((((bp + 0) * 2 + kb) * kBoxBytes + kk * 32) >> 4);
-                                const uint64_t b_im = bdesc + (uint64_t)((((bp + 1) * 2 + kb) * kBoxBytes + kk * 32) >> 4);
+                                const uint64_t b_re = bdesc + (uint64_t)((((bp + 0) * 2 + kb) * kBoxB + kk * 32) >> 4);
+                                const uint64_t b_im = bdesc + (uint64_t)((((bp + 1) * 2 + kb) * kBoxB + kk * 32) >> 4);
                                 const uint32_t a_re = a0 + (ap + 0) * kMaxK + ks * 8;
                                 const uint32_t a_im = a0 + (ap + 1) * kMaxK + ks * 8;
                                 const uint32_t accum = (pass == 0 && ks == 0) ? 0u : 1u;
-                                if (bf || ((prm.debug & 256) && pass == 0)) {
+                                if (k2) {
+                                    if (bf) {
+                                        umma_bf16_ts2(d_re, a_re, b_re, idesc_bf, accum);
+                                        umma_bf16_ts2(d_re, a_im, b_im, idesc_bf_neg, 1u);
+                                        umma_bf16_ts2(d_im, a_re, b_im, idesc_bf, accum);
+                                        umma_bf16_ts2(d_im, a_im, b_re, idesc_bf, 1u);
+                                    } else {
+                                        umma_tf32_ts2(d_re, a_re, b_re, idesc, accum);
+                                        umma_tf32_ts2(d_re, a_im, b_im, idesc_neg, 1u);
+                                        umma_tf32_ts2(d_im, a_re, b_im, idesc, accum);
+                                        umma_tf32_ts2(d_im, a_im, b_re, idesc, 1u);
+                                    }
+                                } else if (bf || ((prm.debug & 256) && pass == 0)) {
                                     umma_bf16_ts(d_re, a_re, b_re, idesc_bf, accum);
                                     umma_bf16_ts(d_re, a_im, b_im, idesc_bf_neg, 1u);
                                     umma_bf16_ts(d_im, a_re, b_im, idesc_bf, accum);
@@ -408,6 +465,14 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                             }
                         }
                     }
+                    if (k2) {
+                        tcgen05_commit_mc2(&bars->b_empty[stage], 3);
+                        tcgen05_commit_mc2(&bars->acc_full[acc], 3);
+                        if (tt == prm.t_tiles - 1) {
+                            tcgen05_commit_mc2(&bars->a_empty, 3);
+                            if (prm.conv_D > 0) red_release_add(prm.done + f, 2);       // both halves have landed
+                        }
+                    } else {
                     if (csize == 1) tcgen05_commit(&bars->b_empty[stage]);
                     else tcgen05_commit_mc(&bars->b_empty[stage], cmask);
                     tcgen05_commit(&bars->acc_full[acc]);
@@ -417,9 +482,10 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         // waited for above): the slot of bin f may be overwritten once all nsl tasks have said so
                         if (prm.conv_D > 0) red_release_add(prm.done + f, 1);
                     }
+                    }
                 }
                 __syncwarp();
-                if (++stage == kStages) {
+                if (++stage == kSt) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -463,7 +529,17 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             long long f;
             int lt;
             decode(grp, f, lt);
-            if (lt >= prm.ltiles) continue;
+            if (lt >= prm.ltiles) {
+                if (k2) {
+                    // ghost tile of a pair: the leader's MMAs cover these rows as well (nobody reads the result);
+                    // keep the operand hand-over alive
+                    mbar_wait(&bars->a_empty, a_phase ^ 1);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(&bars->a_full, 0);
+                    a_phase ^= 1;
+                }
+                continue;
+            }
             float are[32], aim[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) are[j] = aim[j] = 0.f;
@@ -593,7 +669,10 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->a_full);
+            if (lane == 0) {
+                if (k2) mbar_arrive_cta(&bars->a_full, 0);          // the leader's barrier collects both CTAs' builders
+                else mbar_arrive(&bars->a_full);
+            }
             a_phase ^= 1;
         }
     } else {
@@ -602,7 +681,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         // warp owns TMEM lane quarter (warp & 3) = 32 look directions; per frame tile two passes of 32 frames.
         const int quarter = warp & 3;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        unsigned char* const my_store = store_base + (size_t)(warp - kEpiWarp0) * kStoreWarpBytes;
+        unsigned char* const my_store = store_base + (size_t)(warp - kEpiWarp0) * kStoreWarpB;
         // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
         const uint32_t row_off = (uint32_t)lane * 128u;
         const uint32_t sw = (uint32_t)(lane & 7);
@@ -614,7 +693,21 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             long long f;
             int lt;
             decode(grp, f, lt);
-            if (lt >= prm.ltiles) continue;
+            if (lt >= prm.ltiles) {
+                if (k2) {
+                    // ghost tile of a pair: hand every accumulator straight back
+                    for (int tt = 0; tt < prm.t_tiles; ++tt) {
+                        mbar_wait(&bars->acc_full[acc], acc_phase);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cta(&bars->acc_empty[acc], 0);
+                        if (++acc == 2) {
+                            acc = 0;
+                            acc_phase ^= 1;
+                        }
+                    }
+                }
+                continue;
+            }
             const int l0 = lt * kTileL + quarter * 32;
             float psum = 0.f;                                    // sum_t |q[f, l0 + lane, t]|^2
             for (int tt = 0; tt < prm.t_tiles; ++tt) {
@@ -631,7 +724,10 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         // the whole accumulator of this warp's lanes is in registers: release it
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+                        if (lane == 0) {
+                            if (k2) mbar_arrive_cta(&bars->acc_empty[acc], 0);
+                            else mbar_arrive(&bars->acc_empty[acc]);
+                        }
                     }
                     const long long t0 = (long long)tt * kTileT + pass * 32;
                     if (t0 >= prm.T || l0 >= prm.L) continue;                   // warp-uniform
@@ -662,7 +758,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     }
                     unsigned char* const sbuf = my_store + (size_t)buf * 2 * kStoreBoxBytes;
                     // the stores issued from this slot kStoreRing passes ago must have finished reading it
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStoreRing - 1) : "memory");
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kRing - 1) : "memory");
                     __syncwarp();
                     if (!(prm.debug & 4))
 #pragma unroll
@@ -690,7 +786,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    if (++buf == kStoreRing) buf = 0;
+                    if (++buf == kRing) buf = 0;
                 }
                 if (++acc == 2) {
                     acc = 0;
@@ -708,7 +804,8 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     if (csize > 1) cluster_sync_all();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+        if (k2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
     }
 }
 
@@ -1201,6 +1298,8 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     prm.d = d;
     prm.ltiles = (int)ceil_div(Lmain, kTileL);
     prm.csize = (prm.ltiles >= 2 && !options().no_cluster) ? 2 : 1;
+    // CTA pairs on one tcgen05.mma (cta_group::2) instead of two MMA streams sharing a multicast plane stream
+    const bool pair = prm.csize == 2 && options().fused_pair != 0;
     prm.lt_groups = (prm.ltiles + prm.csize - 1) / prm.csize;
     prm.t_tiles = (int)ceil_div(T, kTileT);
     prm.groups = nf * prm.lt_groups;
@@ -1262,7 +1361,8 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     {
         cuuint64_t gdim[3] = {(cuuint64_t)Q, (cuuint64_t)T, (cuuint64_t)(4 * prm.ring)};
         cuuint64_t gstr[2] = {(cuuint64_t)Kp * 4, (cuuint64_t)T * Kp * 4};
-        cuuint32_t box[3] = {(cuuint32_t)kBoxK, (cuuint32_t)kTileT, 1};
+        // (pair mode: a CTA loads its own half of the frame tile)
+        cuuint32_t box[3] = {(cuuint32_t)kBoxK, (cuuint32_t)(pair ? kTileT / 2 : kTileT), 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)Xs, gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1303,7 +1403,9 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
 #else
     prm.debug = 0;
 #endif
-    const size_t smem = (size_t)kStages * kStageBytes + kEpiWarps * kStoreWarpBytes + 256 + kConvSmemBytes + 1024;
+    const size_t smem = (pair ? (size_t)kStages2 * (kStageBytes / 2) + kEpiWarps * (kStoreRing2 * 2 * kStoreBoxBytes)
+                              : (size_t)kStages * kStageBytes + kEpiWarps * kStoreWarpBytes) +
+                        256 + kConvSmemBytes + 1024;
     static_assert(sizeof(Barriers) <= 256, "barrier block");
     const long long grid = n_clusters * prm.csize;
     cudaLaunchConfig_t cfg = {};
@@ -1319,12 +1421,19 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     cudaError_t le;
-#define SFA_FUSED_LAUNCH(HYB, NGV)                                                      \
-    do {                                                                                \
-        SFA_ENSURE_DYN_SMEM((pwd_fused_kernel<HYB, NGV>), smem);                        \
-        prof_begin(st);                                                                 \
-        le = cudaLaunchKernelEx(&cfg, pwd_fused_kernel<HYB, NGV>, xmap, omap, prm);     \
-        prof_end(st);                                                                   \
+#define SFA_FUSED_LAUNCH(HYB, NGV)                                                                  \
+    do {                                                                                            \
+        if (pair) {                                                                                 \
+            SFA_ENSURE_DYN_SMEM((pwd_fused_kernel<HYB, NGV, true>), smem);                          \
+            prof_begin(st);                                                                         \
+            le = cudaLaunchKernelEx(&cfg, pwd_fused_kernel<HYB, NGV, true>, xmap, omap, prm);       \
+            prof_end(st);                                                                           \
+        } else {                                                                                    \
+            SFA_ENSURE_DYN_SMEM((pwd_fused_kernel<HYB, NGV, false>), smem);                         \
+            prof_begin(st);                                                                         \
+            le = cudaLaunchKernelEx(&cfg, pwd_fused_kernel<HYB, NGV, false>, xmap, omap, prm);      \
+            prof_end(st);                                                                           \
+        }                                                                                           \
     } while (0)
     if (Cd <= 9) {
         if (hybrid) SFA_FUSED_LAUNCH(true, 9);

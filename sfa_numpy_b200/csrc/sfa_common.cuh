@@ -76,6 +76,7 @@ struct Options {
     int fft_generic;       // irfft / stft: the generic radix-4 ping-pong kernel instead of the radix-16 fast path
     int reserve_sms;       // SMs the persistent tensor-core kernels leave free (for NCCL's copy kernels when a collective
                            // is meant to run under them)
+    int fused_pair;        // fused kernel: the two CTAs of a cluster as ONE tcgen05.mma.cta_group::2 pair
     int fused_D, fused_ring; // stream-ahead distance / plane-ring size of the fused kernel in bins (0 = automatic)
     int fused_debug;       // timing-attribution switches of the fused kernel; honoured by SFA_DEBUG_HOOKS builds only
 };

@@ -48,6 +48,7 @@ static Options make_options() {
     o.fft_generic = env_flag("SFA_FFT_GENERIC");
     o.reserve_sms = (int)env_num("SFA_RESERVE_SMS", 0.0);
     o.fused_D = (int)env_num("SFA_FUSED_D", 0.0);
+    o.fused_pair = (int)env_num("SFA_FUSED_PAIR", 0.0);
     o.fused_ring = (int)env_num("SFA_FUSED_RING", 0.0);
     o.fused_debug = (int)env_num("SFA_FUSED_DEBUG", 0.0);
     return o;
@@ -200,6 +201,7 @@ static double* option_slot(const char* key, int** islot) {
     else if (!strcmp(key, "fft_generic")) *islot = &o.fft_generic;
     else if (!strcmp(key, "reserve_sms")) *islot = &o.reserve_sms;
     else if (!strcmp(key, "fused_D")) *islot = &o.fused_D;
+    else if (!strcmp(key, "fused_pair")) *islot = &o.fused_pair;
     else if (!strcmp(key, "fused_ring")) *islot = &o.fused_ring;
     else if (!strcmp(key, "fused_debug")) *islot = &o.fused_debug;
     return nullptr;

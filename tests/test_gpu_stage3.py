@@ -574,3 +574,51 @@ def test_pwd_fused_operator_structure_detection(mic, precision):
         q1, q2 = both(Yq_sh, dn, Yp_cw, Xd)
         assert bin_err(cpu(q1), ref) < TOL64 and bin_err(cpu(q2), ref) < TOL64
         assert not torch.equal(q1, q2), ("complex weights: Legendre path not taken", N, Q, L, F, T)
+
+
+@pytest.mark.parametrize("precision", ["c64_fast", "c64"])
+def test_pwd_fused_pair_mode(mic, precision):
+    """The two ways the CTAs of a cluster share one bin: as ONE tcgen05.mma.cta_group::2 pair (M = 256, every CTA
+    holding half of the frame tile) and as two MMA streams behind a multicast plane stream.  Same MMA sequence per
+    output element, so the results must be BIT-equal -- on ragged shapes: odd tile counts (ghost CTA of a pair),
+    frame tails around the 16/32/64-frame boxes, few microphones, the CUDA-core tail rows, power map, map-only
+    runs, enough bins for the stream-ahead conversion."""
+    import torch
+    from sfa_numpy_b200 import _lib
+    S = mic.modal.steering
+    lib = _lib.load()
+    lib.sfa_get_option.restype = ctypes.c_double
+    default_pair = lib.sfa_get_option(b"fused_pair")
+    rng = np.random.default_rng(31)
+    #        N  Q   L    F   T
+    cases = [(3, 16, 256, 2, 64), (3, 20, 300, 5, 70), (4, 36, 385, 7, 130), (2, 12, 700, 4, 18), (7, 64, 2562, 2, 90),
+             (1, 5, 257, 9, 34), (8, 64, 640, 3, 938), (3, 17, 266, 3, 333), (4, 25, 515, 70, 161)]
+    for (N, Q, L, F, T) in cases:
+        az, co, w = O.fibonacci_grid(Q)
+        azl, col, _ = O.fibonacci_grid(L)
+        Yp, Yq = O.sht_matrix(N, az, co, w), O.sht_matrix(N, azl, col)
+        k = O.wavenumbers(128)[:F] + 0.7
+        dn, _ = O.regularize(1 / O.spherical_pw(N, k, 0.042, "rigid"), 100, "Tikh")
+        X = (rng.standard_normal((F, Q, T)) + 1j * rng.standard_normal((F, Q, T))).astype(np.complex64)
+        Xd = torch.from_numpy(X).cuda()
+        res = {}
+        for pair in (0.0, 1.0):
+            try:
+                _lib.check(lib.sfa_set_option(b"fused_pair", pair))
+                plan = S.PwdPlan(Yq, dn, Yp, T, precision=precision, form="steering")
+                q = plan(Xd, power=True).clone()
+                assert lib.sfa_pwd_is_fused(ctypes.byref(plan.shape)), ("not the fused kernel", N, Q, L, F, T)
+                pm = plan.power.clone()
+                pm_only = plan(Xd, power=torch.empty_like(pm), beams=False).clone()
+                q2 = plan(Xd, power=True)
+                assert torch.equal(q, q2)
+                res[pair] = (q, pm, pm_only)
+            finally:
+                lib.sfa_set_option(b"fused_pair", default_pair)
+        sel = sorted(set([0, F // 2, F - 1]))
+        ref = O.pwd_factored(Yq, O.repeat_n_m(dn)[sel], Yp, X[sel].astype(np.complex128))
+        for pair in (0.0, 1.0):
+            assert bin_err(cpu(res[pair][0][sel]), ref) < TOL64, (pair, N, Q, L, F, T, bin_err(cpu(res[pair][0][sel]), ref))
+            assert torch.equal(res[pair][1], res[pair][2]), ("map-only", pair, N, Q, L, F, T)
+        assert torch.equal(res[0.0][0], res[1.0][0]), ("pair vs multicast", N, Q, L, F, T)
+        assert torch.equal(res[0.0][1], res[1.0][1])
