@@ -601,6 +601,10 @@ static int make_plan(const sfa_pwd_shape* s, Plan* p) {
             // against 0.31 ms for the factored form)
             const double build_fma = rows * p->Qp * s->Cd * 8.0 / 30e12;
             // (spherical-harmonic operators with per-order filters are built by the Legendre recurrence: no stream)
+            // (circular-harmonic operators get the rotation build, which takes the table stream away as well -- but on
+            // BASELINE config 2 (33 columns, 360 look directions = 3 tiles + a ghost, T = 256: four short tasks per
+            // bin) the fused kernel still measures 0.54 ms against 0.24 ms for the factored form, so the term stays
+            // for them and keeps the plan on the factored form there)
             const bool leg = s->d_is_per_order && s->Cd >= 2 && s->Cd <= 16;
             const double build_l2 = leg ? 0.0 : rows * p->Qp * s->Cd * 8.0 / 2.5e12;
             const double build = build_fma > build_l2 ? build_fma : build_l2;

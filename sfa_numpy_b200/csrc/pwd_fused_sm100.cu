@@ -166,9 +166,18 @@ __device__ __forceinline__ void st_f32_hint(float* p, float v, uint64_t pol) {
 // Nothing is assumed: the preparation kernel computes s, x and the model in FP64 from the given matrices and
 // records the largest deviation of every G_n from it next to the largest |G_n|; the builders take this path only
 // if every group agrees to 1e-8 (relative to its largest entry), otherwise they read the table as before.
+// The same for circular arrays (circular-harmonic matrices, angular.cht_matrix, one filter per column; orders
+// [0..N, -N..-1]):  G_c[l, q] = s_q z_lq^m(c),  z_lq = e^{i (phi_l - phi_q)}, so
+//     A_f[l, q] = s_q [d_0 + sum_{m=1..N} (d_m + d_{-m}) cos(m D) + i (d_m - d_{-m}) sin(m D)]
+// -- the "rotation build": (cos m D, sin m D) by repeated rotation, 8 FP32 operations per order and entry against
+// 2 N + 1 complex table entries (BASELINE config 2, 33 columns: 1 MB of table per 3 us task, which made the fused
+// kernel slower than the factored form there).  Same FP64 verification, same fallback.
 constexpr int kLegMaxGroups = 16;
-constexpr size_t kLegHdrBytes = 128 * sizeof(unsigned) + 64 * sizeof(float2);      // devmag | s_q ; then xt
+constexpr int kLegHdrWords = 144;                                                  // 64 dev | 64 mag | model | pad
+constexpr size_t kLegHdrBytes = kLegHdrWords * sizeof(unsigned) + 64 * sizeof(float2);      // record | s_q ; then the table
+constexpr int kLegTableRow = 32;                                                   // float4 per look direction and l-tile
 constexpr float kLegTol = 1e-8f;
+enum { kModelNone = 0, kModelLegendre = 1, kModelRotation = 2 };
 
 constexpr int kConvT = 32;                           // frames per conversion tile
 constexpr int kConvSmemBytes = kMaxK * (kConvT + 1) * 8 + kTailMaxRows * kMaxK * 8 + kTailMaxRows * 4;
@@ -210,9 +219,10 @@ struct Params {
     int ring;                    // plane slots: bin f lives in slot f % ring (conv_D > 0); = F otherwise
     float* tail_part;            // [F][nsl][16] partial power sums of the tail rows
     // Addition-theorem build (spherical-harmonic operators, see legendre block below): nullable
-    const unsigned* leg_devmag;  // [64] largest deviation of G_n from s_q (2n+1) P_n(x), [64] largest |G_n| (float bits)
+    const unsigned* leg_devmag;  // [64] largest deviation of G_n from the model, [64] largest |G_n| (float bits), [1] model
     const float2* leg_sq;        // [64] s_q = G_0[., q]
-    const float4* leg_xt;        // [ltiles][16][128] : x[l][4 j .. 4 j + 3] per lane l, x = cos of the angle (l, q)
+    const float4* leg_xt;        // [ltiles][32][128] per lane l: Legendre x[l][4 j .. 4 j + 3] (x = cos of the angle
+                                 // (l, q); the first 16 of a row), rotation (cos, sin)[l][2 j .. 2 j + 1]
     int debug;                   // timing attribution (SFA_DEBUG_HOOKS builds only): 1 no TMA stores, 2 no build FMAs,
                                  // 4 no staging writes, 8 no MMAs, 16 no operand loads, 32 converters read no X,
                                  // 64 converters write no planes
@@ -516,14 +526,17 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         const uint64_t g2_pol = l2_policy_evict_last();
 #endif
         // addition-theorem build: only if the preparation found every group product to follow the Legendre model
-        bool use_leg = false;
-        if (NG > 0 && NG <= kLegMaxGroups && prm.leg_xt != nullptr && prm.ngroups >= 2) {
-            use_leg = true;
+        bool use_leg = false, use_rot = false;
+        if (prm.leg_xt != nullptr && prm.ngroups >= 2) {
+            const unsigned model = __ldg(prm.leg_devmag + 128);
+            bool ok = true;
             for (int g = 0; g < prm.ngroups; ++g) {
                 const float dev = __uint_as_float(__ldg(prm.leg_devmag + g));
                 const float mag = __uint_as_float(__ldg(prm.leg_devmag + 64 + g));
-                if (!(dev <= kLegTol * mag)) use_leg = false;
+                if (!(dev <= kLegTol * mag)) ok = false;
             }
+            use_leg = ok && model == kModelLegendre && NG > 0 && NG <= kLegMaxGroups;
+            use_rot = ok && model == kModelRotation && (prm.ngroups & 1);
         }
         for (long long grp = cluster_id; grp < prm.groups; grp += n_clusters) {
             long long f;
@@ -573,7 +586,57 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     }
                 }
             };
-            if (NG > 0 && NG <= kLegMaxGroups && use_leg) {
+            if (use_rot) {
+                // rotation build (circular-harmonic operators): columns [0..N, -N..-1]
+                if (!(prm.debug & 2)) {
+                    const int ng = prm.ngroups, Nn = (ng - 1) >> 1;
+                    const double2* dF = prm.d + f * ng;
+                    const float2 d0 = ld_filter(dF);
+                    const float4* tr = prm.leg_xt + ((size_t)lt * kLegTableRow + (size_t)half * 16) * kTileL + row;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (half * 32 + h * 16 >= 2 * prm.Kh) continue;          // columns beyond the padded K: zero
+                        float c[16], s[16], C[16], S[16];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 v = __ldg(tr + (size_t)(h * 8 + i) * kTileL);
+                            c[2 * i] = v.x;
+                            s[2 * i] = v.y;
+                            c[2 * i + 1] = v.z;
+                            s[2 * i + 1] = v.w;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            C[e] = c[e];
+                            S[e] = s[e];
+                            are[16 * h + e] = d0.x;
+                            aim[16 * h + e] = d0.y;
+                        }
+#pragma unroll 1
+                        for (int m = 1; m <= Nn; ++m) {
+                            const float2 dp = ld_filter(dF + m), dm = ld_filter(dF + ng - m);
+                            const float ex = dp.x + dm.x, ey = dp.y + dm.y;      // d_m + d_-m
+                            const float ox = dm.y - dp.y, oy = dp.x - dm.x;      // i (d_m - d_-m)
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                are[16 * h + e] = fmaf(ex, C[e], fmaf(ox, S[e], are[16 * h + e]));
+                                aim[16 * h + e] = fmaf(ey, C[e], fmaf(oy, S[e], aim[16 * h + e]));
+                                const float cn = fmaf(C[e], c[e], -S[e] * s[e]);
+                                S[e] = fmaf(S[e], c[e], C[e] * s[e]);
+                                C[e] = cn;
+                            }
+                        }
+                    }
+                    const float2* sq = prm.leg_sq + half * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float2 sv = __ldg(sq + j);
+                        const float r = are[j], i = aim[j];
+                        are[j] = fmaf(r, sv.x, -i * sv.y);
+                        aim[j] = fmaf(r, sv.y, i * sv.x);
+                    }
+                }
+            } else if (NG > 0 && NG <= kLegMaxGroups && use_leg) {
                 // A[l, q] = s_q sum_n (2n + 1) d[n] P_n(x_lq): Legendre recurrence in registers, 16 entries at a time
                 constexpr int NGA = (NG > 0 && NG <= kLegMaxGroups) ? NG : 2;
                 float2 dg[NGA];
@@ -583,7 +646,7 @@ pwd_fused_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     dg[g].x *= (float)(2 * g + 1);
                     dg[g].y *= (float)(2 * g + 1);
                 }
-                const float4* xr = prm.leg_xt + ((size_t)lt * 16 + (size_t)half * 8) * kTileL + row;
+                const float4* xr = prm.leg_xt + ((size_t)lt * kLegTableRow + (size_t)half * 8) * kTileL + row;
                 if (!(prm.debug & 2)) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -1113,8 +1176,8 @@ __device__ __forceinline__ int order_of_col(int i) {     // radial.repeat_n_m: c
 // pairs so that the grid fills the machine.  Reads Y_Q as it is (no conjugate-transposed copy).
 __global__ void __launch_bounds__(kTileL)
 group_products_g2_kernel(const double2* __restrict__ YL, const double2* __restrict__ YQ, long long L, int Q, int M,
-                         int G, int per_order, int Kh, float4* __restrict__ out, unsigned* __restrict__ devmag,
-                         float2* __restrict__ sq_out, float* __restrict__ xt) {
+                         int G, int per_order, int Kh, float4* __restrict__ out, int model,
+                         unsigned* __restrict__ devmag, float2* __restrict__ sq_out, float* __restrict__ xt) {
     extern __shared__ double2 sq[];                              // conj-free copy of Y_Q[q0 .. q1)[m0 .. m1): [q][nm]
     const int lane = threadIdx.x;
     const long long lt = blockIdx.x / G;
@@ -1134,17 +1197,22 @@ group_products_g2_kernel(const double2* __restrict__ YL, const double2* __restri
         sq[i] = (q < Q) ? YQ[(long long)q * M + m0 + mm] : make_double2(0.0, 0.0);
     }
     __syncthreads();
-    // addition-theorem model (devmag != nullptr: per-order groups, M >= 4): s_q = Y_L[0, 0] conj(Y_Q[q, 0]),
-    // x_lq = Re(G_1[l, q] / (3 s_q)), model G_g[l, q] = s_q (2g + 1) P_g(x_lq); everything in FP64
-    const bool leg = devmag != nullptr;
+    // Structure models, everything in FP64, s_q = Y_L[0, 0] conj(Y_Q[q, 0]):
+    //   Legendre (per-order groups, M >= 4): x_lq = Re(G_1[l, q] / (3 s_q)), model G_g[l, q] = s_q (2g + 1) P_g(x_lq)
+    //   rotation (one group per column, M = 2N + 1 >= 3, column c of order m = c or c - M):
+    //            z_lq = G_1[l, q] / s_q, model G_c[l, q] = s_q z^m (m >= 0), s_q conj(z)^|m| (m < 0)
+    const bool leg = model != kModelNone;
     double2 yl1 = make_double2(0.0, 0.0), yl2 = yl1, yl3 = yl1, y00 = yl1;
     if (leg) {
         y00 = YL[0];
         if (l < L) {
             yl1 = YL[l * M + 1];
-            yl2 = YL[l * M + 2];
-            yl3 = YL[l * M + 3];
+            if (model == kModelLegendre) {
+                yl2 = YL[l * M + 2];
+                yl3 = YL[l * M + 3];
+            }
         }
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) devmag[128] = (unsigned)model;
     }
     double ldev = 0.0, lmag = 0.0;
     for (int j = j0; j < j1; ++j) {
@@ -1170,8 +1238,34 @@ group_products_g2_kernel(const double2* __restrict__ YL, const double2* __restri
                 if (q >= Q) continue;
                 const double gre = c ? s2 : s0, gim = c ? s3 : s1;
                 const double2* yq = YQ + (long long)q * M;
-                const double2 q0 = yq[0], q1 = yq[1], q2 = yq[2], q3 = yq[3];
+                const double2 q0 = yq[0], q1 = yq[1];
                 const double sre = y00.x * q0.x + y00.y * q0.y, sim = y00.y * q0.x - y00.x * q0.y;       // y00 conj(q0)
+                if (model == kModelRotation) {
+                    const double h1re = yl1.x * q1.x + yl1.y * q1.y, h1im = yl1.y * q1.x - yl1.x * q1.y;  // G_1[l, q]
+                    const double den = sre * sre + sim * sim;
+                    const double zr = den > 0.0 ? (h1re * sre + h1im * sim) / den : 0.0;                 // G_1 conj(s) / |s|^2
+                    const double zi = den > 0.0 ? (h1im * sre - h1re * sim) / den : 0.0;
+                    const int mo = (g <= (M - 1) / 2) ? g : g - M;
+                    double wr = 1.0, wi = 0.0;
+                    for (int kk = 0; kk < (mo < 0 ? -mo : mo); ++kk) {
+                        const double t = wr * zr - wi * zi;
+                        wi = wr * zi + wi * zr;
+                        wr = t;
+                    }
+                    if (mo < 0) wi = -wi;
+                    const double dre = fabs(gre - (sre * wr - sim * wi)), dim = fabs(gim - (sre * wi + sim * wr));
+                    if (!(dre <= ldev)) ldev = dre;
+                    if (!(dim <= ldev)) ldev = dim;
+                    lmag = fmax(lmag, fmax(fabs(gre), fabs(gim)));
+                    if (g == 1) {
+                        float* tq = xt + (((size_t)lt * kLegTableRow + (q >> 1)) * kTileL + lane) * 4 + (q & 1) * 2;
+                        tq[0] = (float)zr;
+                        tq[1] = (float)zi;
+                    }
+                    if (g == 0 && l == 0) sq_out[q] = make_float2((float)sre, (float)sim);
+                    continue;
+                }
+                const double2 q2 = yq[2], q3 = yq[3];
                 const double g1re = yl1.x * q1.x + yl1.y * q1.y + yl2.x * q2.x + yl2.y * q2.y + yl3.x * q3.x + yl3.y * q3.y;
                 const double g1im = yl1.y * q1.x - yl1.x * q1.y + yl2.y * q2.x - yl2.x * q2.y + yl3.y * q3.x - yl3.x * q3.y;
                 const double den = 3.0 * (sre * sre + sim * sim);
@@ -1189,7 +1283,7 @@ group_products_g2_kernel(const double2* __restrict__ YL, const double2* __restri
                 if (!(dre <= ldev)) ldev = dre;
                 if (!(dim <= ldev)) ldev = dim;
                 lmag = fmax(lmag, fmax(fabs(gre), fabs(gim)));
-                if (g == 1) xt[(((size_t)lt * 16 + (q >> 2)) * kTileL + lane) * 4 + (q & 3)] = (float)x;
+                if (g == 1) xt[(((size_t)lt * kLegTableRow + (q >> 2)) * kTileL + lane) * 4 + (q & 3)] = (float)x;
                 if (g == 0 && l == 0) sq_out[q] = make_float2((float)sre, (float)sim);
             }
         }
@@ -1225,7 +1319,7 @@ static size_t fused_g2_table_bytes(long long L, long long Q, int Cd) {
     return ((size_t)ltiles * Cd * Kh * fused::kTileL * sizeof(float4) + 255) / 256 * 256;
 }
 static size_t fused_leg_bytes(long long L) {
-    return fused::kLegHdrBytes + (size_t)ceil_div(L, fused::kTileL) * 16 * fused::kTileL * sizeof(float4);
+    return fused::kLegHdrBytes + (size_t)ceil_div(L, fused::kTileL) * fused::kLegTableRow * fused::kTileL * sizeof(float4);
 }
 // group-product table + the addition-theorem block (deviation record, s_q, x table)
 size_t pwd_fused_g2_bytes(long long L, long long Q, int Cd) {
@@ -1258,12 +1352,16 @@ int launch_group_products_g2(const double2* YL, const double2* YQ, long long L, 
     // addition-theorem block: zeroed (x = 0, s = 0 for padding rows / columns; deviations start at 0), or -- when the
     // model does not apply -- a deviation record that can never pass (0x7f7f7f7f = 3.4e38 against 1e-8 * 3.4e38)
     unsigned char* legb = reinterpret_cast<unsigned char*>(G2) + fused_g2_table_bytes(L, Q, Cd);
-    const bool leg = per_order && Cd >= 2 && Cd <= fused::kLegMaxGroups && M >= 4 && !options().no_legendre;
+    int model = fused::kModelNone;
+    if (!options().no_legendre) {
+        if (per_order && Cd >= 2 && Cd <= fused::kLegMaxGroups && M >= 4) model = fused::kModelLegendre;
+        else if (!per_order && Cd == M && (M & 1) && M >= 3 && M <= 63) model = fused::kModelRotation;
+    }
     SFA_CUDA_CHECK(cudaMemsetAsync(legb, 0, fused_leg_bytes(L), st));
-    if (!leg) SFA_CUDA_CHECK(cudaMemsetAsync(legb, 0x7f, 128 * sizeof(unsigned), st));
+    if (model == fused::kModelNone) SFA_CUDA_CHECK(cudaMemsetAsync(legb, 0x7f, 128 * sizeof(unsigned), st));
     fused::group_products_g2_kernel<<<dim3((unsigned)(ltiles * Cd), (unsigned)ysplit), fused::kTileL, smem, st>>>(
-        YL, YQ, L, (int)Q, M, Cd, per_order, Kh, reinterpret_cast<float4*>(G2),
-        leg ? reinterpret_cast<unsigned*>(legb) : nullptr, reinterpret_cast<float2*>(legb + 128 * sizeof(unsigned)),
+        YL, YQ, L, (int)Q, M, Cd, per_order, Kh, reinterpret_cast<float4*>(G2), model,
+        reinterpret_cast<unsigned*>(legb), reinterpret_cast<float2*>(legb + fused::kLegHdrWords * sizeof(unsigned)),
         reinterpret_cast<float*>(legb + fused::kLegHdrBytes));
     SFA_LAUNCH_CHECK();
     return SFA_OK;
@@ -1338,7 +1436,7 @@ int launch_pwd_fused(long long nf, long long L, long long Q, long long T, int Cd
     {
         const unsigned char* legb = reinterpret_cast<const unsigned char*>(G2) + fused_g2_table_bytes(L, Q, Cd);
         prm.leg_devmag = reinterpret_cast<const unsigned*>(legb);
-        prm.leg_sq = reinterpret_cast<const float2*>(legb + 128 * sizeof(unsigned));
+        prm.leg_sq = reinterpret_cast<const float2*>(legb + kLegHdrWords * sizeof(unsigned));
         prm.leg_xt = reinterpret_cast<const float4*>(legb + kLegHdrBytes);
     }
     prm.out = out;

@@ -394,6 +394,15 @@ def test_pwd_fused_kernel_shapes(mic, precision):
         plan = S.PwdPlan(Pq, Dn, Pp, T, precision=precision, form="steering")
         q = plan(torch.from_numpy(X).cuda(), power=True)
         assert bin_err(cpu(q[sel]), ref) < TOL64, (N, Q, L, F, T, bin_err(cpu(q[sel]), ref))
+        # circular-harmonic operators: rotation build; the table build must agree with the oracle as well and differ
+        # in the last bits (= the two runs took different paths)
+        try:
+            _lib.check(lib.sfa_set_option(b"no_legendre", 1.0))
+            q_tab = S.PwdPlan(Pq, Dn, Pp, T, precision=precision, form="steering")(torch.from_numpy(X).cuda())
+        finally:
+            lib.sfa_set_option(b"no_legendre", 0.0)
+        assert bin_err(cpu(q_tab[sel]), ref) < TOL64, ("table", N, Q, L, F, T, bin_err(cpu(q_tab[sel]), ref))
+        assert not torch.equal(q, q_tab), ("rotation path not taken", N, Q, L, F, T)
         pm_ref = np.mean(np.abs(ref) ** 2, axis=2)
         assert np.max(np.abs(cpu(plan.power)[sel] - pm_ref) / np.max(pm_ref, axis=1, keepdims=True)) < 1e-5
         q_auto = S.pwd(Pq, Dn, Pp, torch.from_numpy(X).cuda(), precision=precision)       # form chosen by the plan
@@ -568,6 +577,29 @@ def test_pwd_fused_operator_structure_detection(mic, precision):
             q1, q2 = both(Yq, dn, Yp, Xd)
             assert bin_err(cpu(q1), ref) < TOL64, (name, N, Q, L, F, T, bin_err(cpu(q1), ref))
             assert torch.equal(q1, q2), (name, "took the Legendre path", N, Q, L, F, T)
+        # per-column filters (one group per column): random operators, and circular-harmonic matrices whose filters
+        # are NOT symmetric in +-m (the rotation build must not assume d_m = d_-m) or with one perturbed entry
+        Nc = min(2 * N + 3, 15)
+        Mc = 2 * Nc + 1
+        Qc = min(Q, 24)
+        pol = np.linspace(0, 2 * np.pi, Qc, endpoint=False) + 0.1
+        poll = np.sort(rng.random(L)) * 2 * np.pi
+        Pp, Pq = O.cht_matrix(Nc, pol, np.full(Qc, 1.0 / Qc)), O.cht_matrix(Nc, poll)
+        dcol = rng.standard_normal((F, Mc)) + 1j * rng.standard_normal((F, Mc))
+        Xc = (rng.standard_normal((F, Qc, T)) + 1j * rng.standard_normal((F, Qc, T))).astype(np.complex64)
+        Xcd = torch.from_numpy(Xc).cuda()
+        ref = O.pwd_factored(Pq, dcol, Pp, Xc.astype(np.complex128))
+        q1, q2 = both(Pq, dcol, Pp, Xcd)
+        assert bin_err(cpu(q1), ref) < TOL64 and bin_err(cpu(q2), ref) < TOL64, ("circular", bin_err(cpu(q1), ref))
+        assert not torch.equal(q1, q2), ("circular: rotation path not taken", N, Q, L, F, T)
+        Pq_pert = Pq.copy()
+        Pq_pert[L // 3, Mc - 2] *= 1.0 + 1e-6
+        Pq_rand = rng.standard_normal((L, Mc)) + 1j * rng.standard_normal((L, Mc))
+        for name, Yq_c in (("circular perturbed", Pq_pert), ("circular random", Pq_rand)):
+            ref = O.pwd_factored(Yq_c, dcol, Pp, Xc.astype(np.complex128))
+            q1, q2 = both(Yq_c, dcol, Pp, Xcd)
+            assert bin_err(cpu(q1), ref) < TOL64, (name, bin_err(cpu(q1), ref))
+            assert torch.equal(q1, q2), (name, "took the rotation path")
         # complex column weights on the microphone side keep the structure (s_q becomes complex)
         Yp_cw = Yp_sh * np.exp(1j * rng.random((Q, 1)))
         ref = O.pwd_factored(Yq_sh, O.repeat_n_m(dn), Yp_cw, X.astype(np.complex128))
