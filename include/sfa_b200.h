@@ -37,7 +37,9 @@ enum sfa_status {
     SFA_ERR_CUDA = -2,         /* a CUDA runtime/driver call failed (see last error) */
     SFA_ERR_UNSUPPORTED = -3,  /* outside the supported range (e.g. order too large) */
     SFA_ERR_WORKSPACE = -4,    /* caller workspace too small                         */
-    SFA_ERR_NO_DEVICE = -5     /* no sm_100 device                                   */
+    SFA_ERR_NO_DEVICE = -5,    /* no sm_100 device                                   */
+    SFA_ERR_RANGE = -6         /* radial filters beyond the float32 range of the complex64 paths (|d| > 1e30 or
+                                  non-finite): regularise them or use SFA_PREC_C128_FP64 (host-buffer entry points) */
 };
 
 enum sfa_setup { SFA_OPEN = 0, SFA_CARD = 1, SFA_RIGID = 2 };       /* radial.py:146-160 */

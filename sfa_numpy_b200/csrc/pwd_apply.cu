@@ -1016,6 +1016,13 @@ extern "C" int sfa_pwd_host_set_operators(sfa_pwd_host_ctx* c, const sfa_c128* Y
                                           const sfa_c128* d) {
     if (!c || !Y_L || !Y_Q || !d) return SFA_ERR_INVALID;
     const sfa_pwd_shape* s = &c->shape;
+    if (is_c64(s)) {
+        // the complex64 paths narrow the filters to float: |1/b_n| of an unregularised open array near k = 0 would
+        // turn into Inf and the beams into NaN without a word (the reference computes that case in complex128)
+        const double* dv = reinterpret_cast<const double*>(d);
+        for (long long i = 0; i < 2 * s->F * s->Cd; ++i)
+            if (!(fabs(dv[i]) <= 1e30)) return SFA_ERR_RANGE;
+    }
     SFA_CUDA_CHECK(cudaSetDevice(c->device));
     SFA_CUDA_CHECK(cudaMemcpyAsync(c->d_YL, Y_L, (size_t)s->L * s->M * 16, cudaMemcpyHostToDevice, c->s_cmp));
     SFA_CUDA_CHECK(cudaMemcpyAsync(c->d_YQ, Y_Q, (size_t)s->Q * s->M * 16, cudaMemcpyHostToDevice, c->s_cmp));

@@ -230,6 +230,7 @@ const char* sfa_strerror(int status) {
         case SFA_ERR_UNSUPPORTED: return "unsupported size or mode";
         case SFA_ERR_WORKSPACE: return "workspace too small";
         case SFA_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+        case SFA_ERR_RANGE: return "radial filters exceed the float32 range of the complex64 paths";
         default: return "unknown status";
     }
 }

@@ -323,17 +323,22 @@ class PwdHost:
         self.ctx = ctypes.c_void_p()
         _lib.check(self.lib.sfa_pwd_host_create(ctypes.byref(self.ctx), ctypes.byref(self.shape), int(device),
                                                 int(chunk_bins)))
-        _lib.check(self.lib.sfa_pwd_host_set_operators(self.ctx, Y_look.ctypes.data, Y_mic.ctypes.data,
-                                                       dn.ctypes.data))
+        self._pinned = []
+        try:
+            _lib.check(self.lib.sfa_pwd_host_set_operators(self.ctx, Y_look.ctypes.data, Y_mic.ctypes.data,
+                                                           dn.ctypes.data))
+        except Exception:
+            self.close()                         # e.g. SFA_ERR_RANGE: do not leak the context and its device buffers
+            raise
         self.in_shape = (F, Q, int(T))
         self.out_shape = (F, Y_look.shape[0], int(T))
-        self._pinned = []
 
     def set_operators(self, Y_look, dn, Y_mic):
         """Replace the resident operators.  CUDA tensors (the outputs of `angular.sht_matrix` /
         `radial.radial_filters`) are copied device to device; NumPy arrays go through the host path."""
         if all(isinstance(a, torch.Tensor) and a.is_cuda for a in (Y_look, dn, Y_mic)):
             Y_look, dn, Y_mic = (as_complex_tensor(a, a.device) for a in (Y_look, dn, Y_mic))
+            _check_c64_range(dn, "c128" if self.np_dtype == np.complex128 else "c64")
             dev = Y_look.device
             with torch.cuda.device(dev):
                 _lib.check(self.lib.sfa_pwd_host_set_operators_dev(self.ctx, _lib.ptr(Y_look), _lib.ptr(Y_mic),

@@ -38,6 +38,7 @@ def test_status_strings_and_planning(lib):
     assert lib.sfa_version() >= 100
     assert lib.sfa_strerror(0) == b"ok"
     assert b"workspace" in lib.sfa_strerror(-4)
+    assert b"float32 range" in lib.sfa_strerror(-6)
     s = _lib.PwdShape(1024, 2562, 64, 938, 81, 9, 1, 0, 0)
     assert 0 < lib.sfa_pwd_work_bytes(ctypes.byref(s)) < 1 << 30
     bad = _lib.PwdShape(4, 8, 8, 8, 80, 9, 1, 0, 0)           # 9*9 != 80

@@ -230,6 +230,21 @@ def test_pwd_host_path(mic):
     for T in (70, 138):                  # 138 > 128 and not a multiple of 32: row-padded device buffer + 2-D D2H copy
         _host_path_case(S, T)
     _host_path_case(S, 40, N=8, grid=100)    # 100 channels, 81 modes: factored form through the K-loop kernel
+    # filters beyond the float32 range (an unregularised inverse near k = 0): the complex64 host path refuses them
+    # (SFA_ERR_RANGE) instead of returning NaN beams; the complex128 path takes them
+    from sfa_numpy_b200 import _lib
+    az, co, w = O.grid_gauss(2)
+    azl, col, _ = O.fibonacci_grid(50)
+    Yp, Yq = O.sht_matrix(2, az, co, w), O.sht_matrix(2, azl, col)
+    dn = np.ones((3, 3), dtype=complex)
+    dn[1, 2] = 1e35
+    with pytest.raises(_lib.SfaError, match="float32 range"):
+        S.PwdHost(Yq, dn, Yp, 8, precision="c64")
+    dn[1, 2] = np.inf
+    with pytest.raises(_lib.SfaError, match="float32 range"):
+        S.PwdHost(Yq, dn, Yp, 8, precision="c64_fast")
+    dn[1, 2] = 1e35
+    S.PwdHost(Yq, dn, Yp, 8, precision="c128").close()
 
 
 def _host_path_case(S, T, N=4, grid=None):
