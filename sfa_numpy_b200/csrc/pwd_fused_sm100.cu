@@ -12,26 +12,30 @@
 // absorbs at 4.9 TB/s.  Here the roles of the two GEMM operands are swapped:
 //
 //   * TMEM lanes (UMMA M = 128) = 128 look directions l of one bin.  The steering tile A_f[128 l x K<=64 mics]
-//     is the A operand IN TENSOR MEMORY (TS-form tcgen05.mma).  Eight "builder" warps compute it from the
-//     group products G (shared by all bins, L2 resident, stored so that a warp's load is 512 contiguous
-//     bytes) and the bin's radial filters d_f with FP32 FMAs in registers, split it (tf32 hi + lo / packed
-//     bf16) and write the four operand planes with tcgen05.st.  The tile of task i+1 is accumulated in
-//     registers while the MMAs of task i run; only the split + tcgen05.st (a few hundred cycles per ~40k
-//     cycle task) waits for the operand columns to be free.
-//   * UMMA N = 64 frames per step.  The spectra are pre-split once per step into the K-major planes the
-//     tensor core reads (Xs[f][plane][t][q], `x_split_kernel`: 0.5 GB in, 1 GB out) and streamed by TMA
-//     (SWIZZLE_128B, mbarrier complete_tx) into a 2-stage shared-memory ring.  The two CTAs of a cluster
-//     work on two l-tiles of the SAME bin and share that stream: each fetches half of the boxes and
-//     multicasts them.
+//     is the A operand IN TENSOR MEMORY (TS-form tcgen05.mma).  Eight "builder" warps compute it with FP32 FMAs
+//     in registers, split it (tf32 hi + lo / packed bf16) and write the four operand planes with tcgen05.st.
+//     Spherical-harmonic operators: Legendre recurrence on cos(angle(l, q)) (addition theorem; one float per
+//     entry out of L2); circular-harmonic operators: repeated rotation of (cos, sin)(phi_l - phi_q); anything
+//     else: the group products G (shared by all bins, L2 resident, a warp's load is 512 contiguous bytes) times
+//     the bin's radial filters.  Which one is decided per call by an FP64 check of the given matrices (see the
+//     "Addition-theorem build" comment below).  The tile of task i+1 is built while the MMAs of task i run; only
+//     the split + tcgen05.st (a few hundred cycles per ~40k cycle task) waits for the operand columns.
+//   * UMMA N = 64 frames per step.  The spectra are split into the K-major planes the tensor core reads
+//     (Xs[slot][plane][t][q]) by the two spare warps of every CTA, a round of bins AHEAD of the bins being
+//     multiplied, into a ring of plane slots that lives in L2 (`convert_ahead`; launches with few bins use the
+//     pre-pass kernel `x_split_tail_kernel`), and streamed by TMA (SWIZZLE_128B, mbarrier complete_tx) into a
+//     2-stage shared-memory ring.  The two CTAs of a cluster work on two l-tiles of the SAME bin and share that
+//     stream: each fetches half of the boxes and multicasts them.
 //   * One elected thread issues the tcgen05.mma stream (2 passes hybrid / 3 passes 3xTF32 x 4 real products
 //     x K/8 k-steps) into double-buffered (Re, Im) accumulators.
 //   * Four epilogue warps read the accumulators (lane = look direction, columns = frames), transpose them
 //     through warp-private SWIZZLE_128B staging boxes in shared memory (conflict-free 16-byte stores) and
 //     write them with TMA stores.  A CTA owns 128 consecutive rows of out[f] for ALL frames, i.e. over a
-//     task it writes one contiguous ~1 MB region of the beam tensor front to back.
+//     task it writes one contiguous ~1 MB region of the beam tensor front to back; rows end on whole 128-byte
+//     lines when the caller owns the row padding.  The beam power map is accumulated from the same registers.
 //
 // TMEM: 2 x (64 Re + 64 Im) accumulator columns + 4 x 64 operand columns = 512.
-// SMEM: 2 x 64 KB operand stages + 4 x 16 KB store staging.
+// SMEM: 2 x 64 KB operand stages + 4 x 16 KB store staging + 25 KB conversion tile.
 #include <cuda.h>
 #include "sfa_common.cuh"
 #include "sfa_tcgen05.cuh"
