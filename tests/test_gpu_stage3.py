@@ -350,7 +350,9 @@ def test_pwd_fused_kernel_shapes(mic, precision):
     cases = [(2, 9, 5, 3, 2), (3, 16, 128, 2, 64), (3, 20, 129, 5, 70), (4, 36, 300, 7, 130), (2, 12, 700, 4, 18),
              (5, 64, 385, 3, 200), (7, 64, 2562, 2, 90), (1, 5, 257, 9, 34), (8, 64, 130, 3, 938),
              # L mod 128 = 16 (CUDA-core tail kernel, two row groups) and 17 (ragged tensor-core tile + ghost CTA)
-             (3, 20, 144, 2, 40), (3, 20, 145, 2, 40), (3, 17, 266, 3, 333)]
+             (3, 20, 144, 2, 40), (3, 20, 145, 2, 40), (3, 17, 266, 3, 333),
+             # the highest orders of the Legendre build (16 groups: FP32 recurrence up to P_15), near-polar look directions
+             (15, 64, 300, 3, 100), (12, 50, 1000, 2, 64)]
     for (N, Q, L, F, T) in cases:
         az, co, w = O.fibonacci_grid(Q)
         azl, col, _ = O.fibonacci_grid(L)
