@@ -710,8 +710,8 @@ def main():
     achieved = alg_bytes / (gemm_ms_per_step * 1e-3) / 1e9
     launches_per_step = cnt.value / n_prof
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused kernel over 148 bins from the committed
-    # ncu capture (profiles/r4_h_fused_legendre.txt), scaled to this rank's bins; bench.py never runs under ncu.
-    NCU_TRAFFIC_148_BINS = 2.917214e9 + 0.146084e9
+    # ncu capture (profiles/r5_c_fused_final.txt), scaled to this rank's bins; bench.py never runs under ncu.
+    NCU_TRAFFIC_148_BINS = 2.846004e9 + 0.086852e9
     roofline = {"kernel": "pwd_fused_kernel: stage-3 steering build + GEMM in one persistent launch, %s (tcgen05)"
                           % ("hybrid TF32+BF16" if args.precision == "c64_fast" else "3xTF32"),
                 # `bound` / `frac` follow SURVEY 8(d): max(bytes / measured HBM, flops * passes / measured tensor) / t
@@ -727,7 +727,7 @@ def main():
                 "tensor_peak_tflops": tf32_peak,
                 "tensor_peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 rate)",
                 "traffic": NCU_TRAFFIC_148_BINS * nb / 148.0 / max(launches_per_step, 1.0) if args.precision == "c64_fast" else None,
-                "traffic_source": "ncu --set full, one 148-bin launch (profiles/r4_h_fused_legendre.txt), scaled to the launch's bins",
+                "traffic_source": "ncu --set full, one 148-bin launch (profiles/r5_c_fused_final.txt), scaled to the launch's bins",
                 "alg_bytes_per_launch": alg_bytes / launches_per_step if launches_per_step else None,
                 "kernel_ms_per_launch": gemm_ms_per_step / launches_per_step if launches_per_step else None,
                 "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
