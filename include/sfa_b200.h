@@ -70,7 +70,7 @@ int sfa_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* Library-wide tuning knobs (process-global, initialised once at load time from the SFA_<KEY> environment
  * variables; no launch path calls getenv).  Keys: "pwd_chunk_mb" (scratch budget per frequency slab),
- * "no_fused", "no_legendre", "fused_prepass", "fft_generic", "no_dmma", "no_kloop", "no_cluster", "no_fold", "no_tma_store", "old_build" (0/1: switch a kernel
+ * "no_fused", "no_legendre", "kloop_no_hint", "fused_prepass", "fft_generic", "no_dmma", "no_kloop", "no_cluster", "no_fold", "no_tma_store", "old_build" (0/1: switch a kernel
  * variant off -- test and tuning use), "kloop_block", "issuers", "fused_D", "fused_ring" (0 = automatic), "fused_pair" (1: the CTA pairs of the fused kernel on one
  * tcgen05.mma.cta_group::2 stream -- measured slower, off by default),
  * "reserve_sms" (SMs the persistent kernels leave free, e.g. for NCCL copy kernels running under them).  Unknown key: SFA_ERR_INVALID / NaN. */

@@ -86,6 +86,8 @@ struct Params {
     int kchunks;
     int block_chunks, nblocks;    // accumulation blocks (chunks per block, blocks per task)
     float2* scratch;              // [grid][4 lane quarters][128 n][32 rows] running sum of the block partials
+    int store_evict_first;        // output much larger than L2: its stores carry the evict_first policy, so that the
+                                  // written lines do not push the left-operand band and the X / Z chunks out of L2
 };
 
 struct __align__(8) Barriers {
@@ -127,7 +129,16 @@ __device__ __forceinline__ void store_columns(const Params& prm, uint32_t (&re)[
         }
     }
     float2* o = out_bm + nbase * prm.ldo;
-    if (ncols == 32) {
+    if (ncols == 32 && prm.store_evict_first) {
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(o), "r"(re[j]), "r"(im[j]), "l"(pol)
+                         : "memory");
+            o += prm.ldo;
+        }
+    } else if (ncols == 32) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             *o = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
@@ -515,6 +526,7 @@ int launch_cgemm3x_kloop(long long B, long long Nn, long long Mm, long long K, c
     prm.strideR = strideR;
     prm.out = out;
     prm.ldo = ldo;
+    prm.store_evict_first = (options().kloop_no_hint == 0 && (double)B * (double)Nn * (double)ldo * 8.0 > 256e6) ? 1 : 0;
     prm.strideO = strideO;
     prm.rowscale = rowscale;
     prm.strideS = strideS;

@@ -65,6 +65,7 @@ struct Options {
     int no_cluster;        // no CTA pairs / TMA multicast
     int no_fold;           // resident-K kernel: do not fold bins into the frame tiles
     int no_tma_store;      // resident-K kernel: register stores instead of the TMA-store epilogue
+    int kloop_no_hint;     // K-loop kernel: plain output stores (no evict_first policy on large outputs)
     int kloop_block;       // accumulation block of the K-loop kernel in 32-k chunks (0 = default)
     int issuers;           // MMA issuer warps of the resident-K kernel (1 or 2)
     int old_build;         // steering build: generic kernel instead of the few-groups fast kernel

@@ -39,6 +39,7 @@ static Options make_options() {
     o.no_fold = env_flag("SFA_NO_FOLD");
     o.no_tma_store = env_flag("SFA_NO_TMA_STORE");
     o.kloop_block = (int)env_num("SFA_KLOOP_BLOCK", 0.0);
+    o.kloop_no_hint = env_flag("SFA_KLOOP_NO_HINT");
     o.issuers = ((int)env_num("SFA_ISSUERS", 1.0) == 2) ? 2 : 1;
     o.old_build = env_flag("SFA_OLD_BUILD");
     o.no_fused = env_flag("SFA_NO_FUSED");
@@ -192,6 +193,7 @@ static double* option_slot(const char* key, int** islot) {
     else if (!strcmp(key, "no_fold")) *islot = &o.no_fold;
     else if (!strcmp(key, "no_tma_store")) *islot = &o.no_tma_store;
     else if (!strcmp(key, "kloop_block")) *islot = &o.kloop_block;
+    else if (!strcmp(key, "kloop_no_hint")) *islot = &o.kloop_no_hint;
     else if (!strcmp(key, "issuers")) *islot = &o.issuers;
     else if (!strcmp(key, "old_build")) *islot = &o.old_build;
     else if (!strcmp(key, "no_fused")) *islot = &o.no_fused;
