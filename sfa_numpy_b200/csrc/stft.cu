@@ -294,8 +294,12 @@ stft_kernel(const StftParams prm, const R* __restrict__ x, const R* __restrict__
 // ------------------------------------------------------------------------------------------------------------
 namespace fast {
 
+// 256 threads: the radix-16 butterflies with their composed twiddles want ~240 registers; with 512 threads (128
+// registers) the passes spilled 260 bytes per thread.  256 threads without spills measure 6-15 % faster on every
+// length (n = 2048: 2.31 -> 2.16 ms on the headline shape, n = 256: 6.08 -> 5.18 ms, STFT 0.83 -> 0.77 ms); 384
+// threads (168 registers, 104 bytes of spills, uneven rounds) are slower than both.
 #ifndef SFA_FFT_THREADS
-#define SFA_FFT_THREADS 512
+#define SFA_FFT_THREADS 256
 #endif
 #ifndef SFA_FFT_PAIRS
 #define SFA_FFT_PAIRS 8
