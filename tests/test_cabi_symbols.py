@@ -121,3 +121,29 @@ def test_grid_lebedev_surface():
     except ImportError:
         with pytest.raises(ImportError):
             angular.grid_lebedev(4)
+
+
+def test_header_is_plain_c_and_struct_layout_matches_ctypes(tmp_path):
+    """include/sfa_b200.h must compile as C (the drop-in boundary is a C ABI) and the ctypes mirror of
+    sfa_pwd_shape must have the compiler's layout: a field added on one side only would shift every argument."""
+    import shutil
+    import subprocess
+    from sfa_numpy_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    fields = [name for name, _ in _lib.PwdShape._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "sfa_b200.h"', 'int main(void) {',
+            '  printf("size %zu\\n", sizeof(sfa_pwd_shape));']
+    prog += ['  printf("%s %%zu\\n", offsetof(sfa_pwd_shape, %s));' % (f, f) for f in fields]
+    prog += ['  printf("c128 %zu c64 %zu\\n", sizeof(sfa_c128), sizeof(sfa_c64));', '  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    assert out[0] == "size %d" % ctypes.sizeof(_lib.PwdShape)
+    for line, f in zip(out[1:], fields):
+        assert line == "%s %d" % (f, getattr(_lib.PwdShape, f).offset), line
+    assert out[1 + len(fields)] == "c128 16 c64 8"
