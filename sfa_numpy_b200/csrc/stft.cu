@@ -530,6 +530,20 @@ irfft_fast_kernel(const IrfftParams prm, const cf* __restrict__ q, float* __rest
         __syncthreads();
         fft_inplace<true>(data, sstride, tw, m, prm.log2m, nseq);
         // unpack: x_a[j] = Re z[j] / n, x_b[j] = Im z[j] / n
+        // (whole tiles whose rows are 16-byte aligned: two sequences = four real columns per store)
+        if (nseq >= 2 && c0 + cols <= prm.C && ((prm.ldo | c0) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+            const int hs = nseq >> 1, lgh = lg - 1;
+#pragma unroll 4
+            for (int w = threadIdx.x; w < n * hs; w += kT) {
+                const int j = w >> lgh, s = (w & (hs - 1)) << 1;
+                const cf z0 = data[(size_t)s * sstride + pad_idx(j)];
+                const cf z1 = data[(size_t)(s + 1) * sstride + pad_idx(j)];
+                int jo = j + prm.shift;
+                if (jo >= n) jo -= n;
+                *reinterpret_cast<float4*>(out + (long long)jo * prm.ldo + c0 + 2 * s) =
+                    make_float4(z0.x * scale, z0.y * scale, z1.x * scale, z1.y * scale);
+            }
+        } else
 #pragma unroll 4
         for (int w = threadIdx.x; w < n * nseq; w += kT) {
             const int j = w >> lg, s = w & (nseq - 1);
@@ -566,6 +580,27 @@ stft_fast_kernel(const StftParams prm, const float* __restrict__ x, const float*
         const long long t0 = (tile - qi * ttiles) * frames;
         __syncthreads();
         const float* xq = x + qi * prm.S;
+        // four consecutive samples per load when everything is 16-byte aligned (hop and signal length multiples of 4):
+        // a quarter of the load instructions of the scalar loop below
+        const bool vec4 = ((prm.hop & 3) == 0) && ((prm.S & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                          (!win || (reinterpret_cast<uintptr_t>(win) & 15) == 0);
+        if (vec4) {
+            const int lq = prm.log2n - 2;
+#pragma unroll 4
+            for (int w = threadIdx.x; w < nseq * (n >> 2); w += kT) {
+                const int s = w >> lq, j = (w & ((n >> 2) - 1)) << 2;
+                const long long ta = t0 + 2 * s, tb = ta + 1;
+                const float4 wv = win ? __ldg(reinterpret_cast<const float4*>(win + j)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 va = (ta < prm.T) ? __ldg(reinterpret_cast<const float4*>(xq + ta * prm.hop + j)) : z4;
+                const float4 vb = (tb < prm.T) ? __ldg(reinterpret_cast<const float4*>(xq + tb * prm.hop + j)) : z4;
+                cf* d = data + (size_t)s * sstride + pad_idx(j);             // j .. j + 3 lie in one 16-entry block
+                d[0] = mk<float>(va.x * wv.x, vb.x * wv.x);
+                d[1] = mk<float>(va.y * wv.y, vb.y * wv.y);
+                d[2] = mk<float>(va.z * wv.z, vb.z * wv.z);
+                d[3] = mk<float>(va.w * wv.w, vb.w * wv.w);
+            }
+        } else
 #pragma unroll 8
         for (int w = threadIdx.x; w < nseq * n; w += kT) {
             const int s = w >> prm.log2n, j = w & (n - 1);      // j fastest: coalesced along the signal
@@ -586,8 +621,12 @@ stft_fast_kernel(const StftParams prm, const float* __restrict__ x, const float*
             const cf xb = mk<float>(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
             const long long ta = t0 + 2 * s;
             cf* o = X + ((long long)k * prm.Q + qi) * prm.T + ta;
-            if (ta < prm.T) o[0] = xa;
-            if (ta + 1 < prm.T) o[1] = xb;
+            if (ta + 1 < prm.T && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                *reinterpret_cast<float4*>(o) = make_float4(xa.x, xa.y, xb.x, xb.y);     // frames ta, ta + 1: 16 bytes
+            } else {
+                if (ta < prm.T) o[0] = xa;
+                if (ta + 1 < prm.T) o[1] = xb;
+            }
         }
     }
 }
